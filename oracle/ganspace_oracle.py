@@ -1,0 +1,398 @@
+"""ORACLE -- test infrastructure only.
+
+CPU restatement (numpy + the plain-C RNG in ``mt19937_legacy.c``) of the reference's
+activation-sampling + incremental-PCA hot path.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s cpu_baseline / ``--impl reference`` legs may import this module; the product package
+``ganspace_b200`` never does (tests/test_no_oracle_in_product.py enforces it).
+
+Every function cites the reference file:line it follows (paths relative to /root/reference).
+
+Parity pinning: the reference holds no golden vectors for this path that can be
+regenerated offline, so the oracle is pinned against *outputs of the reference itself run in the
+build container*: ``oracle/gen_golden.py`` imports the unmodified reference (``decomposition.py``,
+``models/wrappers.py``, the vendored StyleGAN2 generator) plus scikit-learn 1.9.0 /
+NumPy 2.3.5 / SciPy 1.18.1, and writes the fixtures under ``tests/golden/``;
+``tests/test_oracle_golden.py`` checks this restatement against them.
+
+Third-party arithmetic restated here (absent from /root/reference, un-pinned by environment.yml:14-15):
+  * NumPy legacy RandomState (MT19937, polar normals, masked randint)      -> mt19937_legacy.c
+  * scikit-learn IncrementalPCA.partial_fit / _incremental_mean_and_var / svd_flip
+      sklearn/decomposition/_incremental_pca.py:254-380, sklearn/utils/extmath.py:1118-1265,924-982
+  * scipy.linalg.lstsq(gelsd) (decomposition.py:133), scipy.stats.truncnorm.rvs (biggan utils.py:32)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+
+def build_c(force: bool = False) -> Path:
+    """Compile the C restatement (gcc) into oracle/_build/."""
+    out = _HERE / "_build" / "libmt19937_legacy.so"
+    src = _HERE / "mt19937_legacy.c"
+    if force or not out.exists() or out.stat().st_mtime < src.stat().st_mtime:
+        out.parent.mkdir(exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off",
+                               "-o", str(out), str(src), "-lm"])
+    return out
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(str(build_c()))
+    return _LIB
+
+
+# --------------------------------------------------------------------------------------------
+# RNG  (models/wrappers.py:167-175; decomposition.py:226-227)
+# --------------------------------------------------------------------------------------------
+INT32_MAX = 2147483647
+
+
+def seed_sequence(seed0: int, count: int) -> np.ndarray:
+    """np.random.seed(seed0); [np.random.randint(np.iinfo(np.int32).max) for _ in range(count)]
+    -- the per-call seeds StyleGAN2.sample_latent draws from the global state (wrappers.py:168-169)."""
+    out = np.empty(count, np.uint32)
+    _lib().gso_randint_sequence(ctypes.c_uint32(seed0), ctypes.c_uint32(INT32_MAX),
+                                ctypes.c_int64(count), out.ctypes.data_as(ctypes.c_void_p))
+    return out
+
+
+def standard_normal_f32(seed: int, n: int) -> np.ndarray:
+    """RandomState(seed).standard_normal(n) cast to float32 (wrappers.py:171-174)."""
+    out = np.empty(n, np.float32)
+    _lib().gso_standard_normal_f32(ctypes.c_uint32(seed), ctypes.c_int64(n),
+                                   out.ctypes.data_as(ctypes.c_void_p))
+    return out
+
+
+def standard_normal_f64(seed: int, n: int) -> np.ndarray:
+    out = np.empty(n, np.float64)
+    _lib().gso_standard_normal_f64(ctypes.c_uint32(seed), ctypes.c_int64(n),
+                                   out.ctypes.data_as(ctypes.c_void_p))
+    return out
+
+
+def random_sample_f64(seed: int, n: int) -> np.ndarray:
+    out = np.empty(n, np.float64)
+    _lib().gso_random_sample_f64(ctypes.c_uint32(seed), ctypes.c_int64(n),
+                                 out.ctypes.data_as(ctypes.c_void_p))
+    return out
+
+
+def raw_u32(seed: int, n: int) -> np.ndarray:
+    out = np.empty(n, np.uint32)
+    _lib().gso_raw_u32(ctypes.c_uint32(seed), ctypes.c_int64(n), out.ctypes.data_as(ctypes.c_void_p))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# StyleGAN2 mapping network  (stylegan2-pytorch/model.py:14-19,132-161,400-409; op/fused_act.py:86-92)
+# --------------------------------------------------------------------------------------------
+LR_MLP = 0.01
+SQRT2_F32 = np.float32(2 ** 0.5)
+
+
+def mapping_random_init(seed: int = 1234, n_mlp: int = 8, dim: int = 512):
+    """The random-init mapping weights the BASELINE configs name: ``torch.manual_seed(seed)`` followed
+    by ``Generator(size, 512, 8)`` -- the mapping EqualLinear weights are the first RNG consumers
+    (model.py:400-409, weight = randn(out,in)/lr_mul :138, bias = 0 :141)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    ws = [torch.randn(dim, dim, generator=g).div_(LR_MLP).numpy() for _ in range(n_mlp)]
+    bs = [np.zeros(dim, np.float32) for _ in range(n_mlp)]
+    return ws, bs
+
+
+def pixel_norm(x: np.ndarray) -> np.ndarray:
+    """model.py:14-19  input * rsqrt(mean(input**2, dim=1) + 1e-8), float32."""
+    x = x.astype(np.float32, copy=False)
+    ms = np.mean(x * x, axis=1, keepdims=True, dtype=np.float32) + np.float32(1e-8)
+    return (x * (np.float32(1.0) / np.sqrt(ms))).astype(np.float32)
+
+
+def mapping_forward(z: np.ndarray, weights, biases, lr_mul: float = LR_MLP) -> np.ndarray:
+    """Generator.style: PixelNorm then 8x EqualLinear(activation='fused_lrelu')
+    (model.py:151-161: F.linear(x, W*scale) ; fused_leaky_relu(out, bias*lr_mul) = sqrt2*lrelu_0.2(out+b))."""
+    x = pixel_norm(z)
+    for w, b in zip(weights, biases):
+        scale = np.float32((1.0 / np.sqrt(w.shape[1])) * lr_mul)
+        ws = (w.astype(np.float32) * scale).astype(np.float32)
+        y = x @ ws.T + (b.astype(np.float32) * np.float32(lr_mul))
+        y = np.where(y >= 0, y, y * np.float32(0.2)).astype(np.float32)
+        x = (SQRT2_F32 * y).astype(np.float32)
+    return x
+
+
+# --------------------------------------------------------------------------------------------
+# Incremental PCA  (estimators.py:55-81 -> sklearn IncrementalPCA.partial_fit)
+# --------------------------------------------------------------------------------------------
+class IPCAState:
+    def __init__(self, n_components: int):
+        self.n_components = n_components
+        self.n_samples_seen = 0
+        self.mean = 0.0
+        self.var = 0.0
+        self.components = None
+        self.singular_values = None
+        self.explained_variance = None
+        self.explained_variance_ratio = None
+
+
+def incremental_mean_and_var(X, last_mean, last_var, last_n):
+    """sklearn/utils/extmath.py:1118-1265 (no NaNs, no sample weights), float64 accumulators."""
+    X64 = X.astype(np.float64)
+    n_new = X.shape[0]
+    last_sum = last_mean * last_n
+    new_sum = X64.sum(axis=0)
+    n_tot = last_n + n_new
+    mean = (last_sum + new_sum) / n_tot
+    T = new_sum / n_new
+    temp = X64 - T
+    corr = temp.sum(axis=0)
+    new_unnorm = (temp ** 2).sum(axis=0) - corr ** 2 / n_new
+    if last_n == 0:
+        unnorm = new_unnorm
+    else:
+        last_unnorm = last_var * last_n
+        r = last_n / n_new
+        unnorm = last_unnorm + new_unnorm + r / n_tot * (last_sum / r - new_sum) ** 2
+    return mean, unnorm / n_tot, n_tot
+
+
+def svd_flip_v(Vt):
+    """sklearn svd_flip(u_based_decision=False): the largest-|.| entry of each row becomes positive."""
+    idx = np.argmax(np.abs(Vt), axis=1)
+    signs = np.sign(Vt[np.arange(Vt.shape[0]), idx])
+    return Vt * signs[:, None], signs
+
+
+def ipca_partial_fit(st: IPCAState, X: np.ndarray) -> IPCAState:
+    """sklearn/decomposition/_incremental_pca.py:254-380 restated (SVD form, dtype behaviour kept:
+    first batch float32 SVD, stacked matrix float64 afterwards)."""
+    import scipy.linalg
+    X = np.array(X, copy=True)
+    n_samples = X.shape[0]
+    col_mean, col_var, n_total = incremental_mean_and_var(X, st.mean, st.var, st.n_samples_seen)
+    if st.n_samples_seen == 0:
+        X -= col_mean
+    else:
+        col_batch_mean = np.mean(X, axis=0)
+        X -= col_batch_mean
+        mean_correction = np.sqrt((st.n_samples_seen / n_total) * n_samples) * (st.mean - col_batch_mean)
+        X = np.vstack((st.singular_values.reshape((-1, 1)) * st.components, X, mean_correction))
+    U, S, Vt = scipy.linalg.svd(X, full_matrices=False, check_finite=False)
+    Vt, _ = svd_flip_v(Vt)
+    c = st.n_components
+    st.explained_variance = (S ** 2 / (n_total - 1))[:c]
+    st.explained_variance_ratio = (S ** 2 / np.sum(col_var * n_total))[:c]
+    st.n_samples_seen = n_total
+    st.components = Vt[:c]
+    st.singular_values = S[:c]
+    st.mean = col_mean
+    st.var = col_var
+    return st
+
+
+def batch_stats(X: np.ndarray):
+    """Per-batch sufficient statistics of the Gram-form chain: (n, mean[d], centred Gram[d,d]) in fp64."""
+    X64 = X.astype(np.float64)
+    m = X64.mean(axis=0)
+    Xc = X64 - m
+    return X.shape[0], m, Xc.T @ Xc
+
+
+def ipca_gram_step(st: IPCAState, n_b: int, mean_b: np.ndarray, gram_b: np.ndarray) -> IPCAState:
+    """Gram-form restatement of one partial_fit:
+        G = V^T S^2 V + Xc^T Xc + m m^T,  m = sqrt(n_seen*n_b/n_tot) (mean - mean_b)
+    eigh(G) -> top-c (lambda, v); S = sqrt(lambda); sign rule of svd_flip.  The running mean/var merge is
+    Chan et al. exactly as _incremental_mean_and_var does it, using diag(Xc^T Xc) as the batch's
+    unnormalised variance."""
+    c = st.n_components
+    n_tot = st.n_samples_seen + n_b
+    new_unnorm = np.diag(gram_b).copy()
+    if st.n_samples_seen == 0:
+        G = gram_b.copy()
+        mean = mean_b.copy()
+        unnorm = new_unnorm
+    else:
+        V, S = st.components.astype(np.float64), st.singular_values.astype(np.float64)
+        m = np.sqrt((st.n_samples_seen / n_tot) * n_b) * (st.mean - mean_b)
+        G = (V.T * (S ** 2)) @ V + gram_b + np.outer(m, m)
+        mean = (st.mean * st.n_samples_seen + mean_b * n_b) / n_tot
+        unnorm = st.var * st.n_samples_seen + new_unnorm + \
+            (st.n_samples_seen * n_b / n_tot) * (st.mean - mean_b) ** 2
+    lam, Q = np.linalg.eigh(G)
+    lam = lam[::-1][:c]
+    Vt = Q[:, ::-1][:, :c].T
+    Vt, _ = svd_flip_v(Vt)
+    S = np.sqrt(np.maximum(lam, 0.0))
+    st.components = Vt
+    st.singular_values = S
+    st.explained_variance = S ** 2 / (n_tot - 1)
+    st.explained_variance_ratio = S ** 2 / np.sum(unnorm)
+    st.mean = mean
+    st.var = unnorm / n_tot
+    st.n_samples_seen = n_tot
+    return st
+
+
+# --------------------------------------------------------------------------------------------
+# decomposition.compute  (decomposition.py:150-358) for StyleGAN2 layer='style'
+# --------------------------------------------------------------------------------------------
+SEED_SAMPLING, SEED_RANDOM_DIRS, SEED_LINREG = 1, 2, 3   # decomposition.py:34-37
+
+
+def plan(n: int, B: int, c: int):
+    """decomposition.py:201,220,232:  N, NB, n_lat, number of partial_fit groups."""
+    N = n // B * B
+    NB = max(B, max(2000, 3 * c))
+    n_lat = ((N + NB - 1) // B + 1) * B
+    K = (N + NB - 1) // NB
+    return N, NB, n_lat, K
+
+
+def get_random_dirs(components: int, dimensions: int) -> np.ndarray:
+    """decomposition.py:42-46."""
+    gen = np.random.RandomState(seed=SEED_RANDOM_DIRS)
+    dirs = gen.normal(size=(components, dimensions))
+    dirs /= np.sqrt(np.sum(dirs ** 2, axis=1, keepdims=True))
+    return dirs.astype(np.float32)
+
+
+class _GlobalSeeds:
+    """The module-level NumPy state the reference threads through sample_latent calls."""
+
+    def __init__(self, seed0):
+        self.seed0, self.i, self._cache = seed0, 0, np.empty(0, np.uint32)
+
+    def next(self):
+        if self.i >= len(self._cache):
+            self._cache = seed_sequence(self.seed0, max(64, 2 * (self.i + 1)))
+        s = int(self._cache[self.i])
+        self.i += 1
+        return s
+
+
+def compute_stylegan2_style(weights, biases, n: int, B: int, c: int, use_w: bool, seed=None,
+                            ipca: str = "svd", return_aux: bool = False):
+    """Restated decomposition.compute (:150-341) for model=StyleGAN2, layer='style', estimator='ipca'.
+    ``ipca``: 'svd' = sklearn-form partial_fit restatement, 'gram' = Gram-chain restatement."""
+    d = 512
+    c = min(c, d)                                                    # :191
+    N, NB, n_lat, K = plan(n, B, c)
+    seeds = _GlobalSeeds(seed or SEED_SAMPLING)                      # :226-227
+
+    # Phase A (:232-236): one sample_latent(B) per micro-batch; W-space applies the mapping here
+    latents = np.zeros((n_lat, d), np.float32)
+    for i in range(n_lat // B):
+        z = standard_normal_f32(seeds.next(), d * B).reshape(B, d)
+        latents[i * B:(i + 1) * B] = mapping_forward(z, weights, biases) if use_w else z
+
+    # Phase B (:239-265)
+    st = IPCAState(c)
+    X = None
+    for gi in range(0, N, NB):
+        rows = latents[gi:gi + NB]
+        X = (rows if use_w else mapping_forward(rows, weights, biases)).astype(np.float32).copy()
+        if ipca == "svd":
+            ipca_partial_fit(st, X)
+        else:
+            ipca_gram_step(st, *batch_stats(X))
+
+    X_global_mean = st.mean.reshape(1, d)                            # :289
+    X = (X.astype(np.float64) - X_global_mean).astype(np.float32)    # :291 (float32 array -= float64)
+    X_comp = np.array(st.components, dtype=np.float64, copy=True)
+    X_stdev = np.sqrt(st.explained_variance)
+    X_var_ratio = st.explained_variance_ratio
+
+    if use_w:                                                        # samples_are_latents (:239,297-299)
+        Z_comp, Z_mean = X_comp, X_global_mean
+    else:                                                            # :301-305 -> linreg_lstsq :77-139
+        Z_comp, Z_mean = linreg_style(weights, biases, X_comp, X_global_mean, X_stdev, n, B)
+    Z_comp = Z_comp / np.linalg.norm(Z_comp, axis=-1, keepdims=True)  # :308
+    if use_w:
+        X_comp = Z_comp                                              # same ndarray in the reference
+
+    random_dirs = get_random_dirs(c, d)                              # :312
+    n_rand = min(5000, X.shape[0])
+    X_stdev_random = np.dot(random_dirs, X[:n_rand].T).std(axis=1)   # :313-316
+
+    lat_stdev = np.ones_like(X_stdev)                                # :325
+    aux = {}
+    if use_w:                                                        # :326-329
+        z = standard_normal_f32(seeds.next(), d * 5000).reshape(5000, d)
+        samples = mapping_forward(z, weights, biases)
+        coords = np.dot(Z_comp.reshape(-1, d), samples.T)
+        lat_stdev = coords.std(axis=1)
+
+    out = {                                                          # :331-341
+        "act_comp": X_comp.reshape(-1, 1, d).astype(np.float32),
+        "act_mean": X_global_mean.reshape(1, d).astype(np.float32),
+        "act_stdev": X_stdev.astype(np.float32),
+        "lat_comp": Z_comp.reshape(-1, 1, d).astype(np.float32),
+        "lat_mean": np.asarray(Z_mean).reshape(1, d).astype(np.float32),
+        "lat_stdev": lat_stdev.astype(np.float32),
+        "var_ratio": X_var_ratio.astype(np.float32),
+        "random_stdevs": X_stdev_random.astype(np.float32),
+    }
+    if return_aux:
+        aux.update(state=st, N=N, NB=NB, n_lat=n_lat, K=K)
+        return out, aux
+    return out
+
+
+def linreg_style(weights, biases, comp, mean, stdev, n: int, B: int):
+    """decomposition.py:77-139 for layer='style' in Z space: regress latent z on scaled PC coordinates."""
+    import scipy.linalg
+    seeds = _GlobalSeeds(SEED_LINREG)                                # :80-81
+    seeds.next()   # :88 get_latent_dims() -> get_latent_shape() -> sample_latent(1) eats one global draw
+    comp32 = comp.astype(np.float32)
+    mean32 = np.asarray(mean).astype(np.float32).reshape(1, -1)
+    stdev32 = stdev.astype(np.float32)
+    n_samp = max(10_000, n) // B * B                                 # :87
+    A = np.zeros((n_samp, comp.shape[0]), np.float32)
+    Z = np.zeros((n_samp, 512), np.float32)
+    for i in range(n_samp // B):                                     # :115-126
+        z = standard_normal_f32(seeds.next(), 512 * B).reshape(B, 512)
+        act = mapping_forward(z, weights, biases) - mean32
+        coords = act @ comp32.T
+        A[i * B:(i + 1) * B] = coords / stdev32
+        Z[i * B:(i + 1) * B] = z
+    M_t = scipy.linalg.lstsq(A, Z, lapack_driver="gelsd")[0]        # :133
+    return M_t[:comp.shape[0], :].astype(np.float64), np.mean(Z, axis=0, keepdims=True)
+
+
+# --------------------------------------------------------------------------------------------
+# comparison metric of BASELINE.json (sign-normalised cosine, explained-variance ratios)
+# --------------------------------------------------------------------------------------------
+def compare_npz(ours: dict, ref: dict) -> dict:
+    a = np.asarray(ours["act_comp"], np.float64).reshape(ours["act_comp"].shape[0], -1)
+    b = np.asarray(ref["act_comp"], np.float64).reshape(ref["act_comp"].shape[0], -1)
+    cos = np.sum(a * b, axis=1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1))
+    la = np.asarray(ours["lat_comp"], np.float64).reshape(a.shape[0], -1)
+    lb = np.asarray(ref["lat_comp"], np.float64).reshape(a.shape[0], -1)
+    lcos = np.sum(la * lb, axis=1) / (np.linalg.norm(la, axis=1) * np.linalg.norm(lb, axis=1))
+
+    def rel(k):
+        x, y = np.asarray(ours[k], np.float64), np.asarray(ref[k], np.float64)
+        return float(np.max(np.abs(x - y)) / max(np.max(np.abs(y)), 1e-30))
+
+    return {
+        "min_abs_cos": float(np.min(np.abs(cos))),
+        "min_signed_cos": float(np.min(cos)),
+        "min_lat_signed_cos": float(np.min(lcos)),
+        "max_abs_dvar_ratio": float(np.max(np.abs(np.asarray(ours["var_ratio"], np.float64) -
+                                                  np.asarray(ref["var_ratio"], np.float64)))),
+        "act_mean_rel": rel("act_mean"), "act_stdev_rel": rel("act_stdev"),
+        "lat_mean_rel": rel("lat_mean"), "lat_stdev_rel": rel("lat_stdev"),
+        "random_stdevs_rel": rel("random_stdevs"),
+    }

@@ -1,0 +1,148 @@
+"""ORACLE -- generator of the committed golden fixtures (tests/golden/*.npz).
+
+Runs the UNMODIFIED reference (/root/reference: decomposition.get_or_compute, models.wrappers.StyleGAN2,
+the vendored stylegan2-pytorch Generator, estimators.IPCAEstimator -> scikit-learn IncrementalPCA) on
+CPU in the build container and stores its outputs.  /root/reference does not exist on the GPU box, so
+nothing at test/bench time imports it -- only these small fixtures travel.
+
+Recipe = SURVEY.md Appendix A: four sys.modules stubs for absent non-hot-path imports (fbpca, skimage,
+boto3, botocore) and a random-init ``load_model`` override (no network for checkpoints; BASELINE.json
+configs say "random-init weights").  Nothing else about the reference is modified.
+
+Usage:  python oracle/gen_golden.py            (writes tests/golden/, prints oracle-vs-reference deltas)
+"""
+import os
+import sys
+import types
+import tempfile
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parents[1]
+REF = os.environ.get("GANSPACE_REFERENCE", "/root/reference")
+OUT = REPO / "tests" / "golden"
+
+
+def _import_reference():
+    sys.path.insert(0, REF)
+
+    def stub(name, **a):
+        m = types.ModuleType(name)
+        m.__dict__.update(a)
+        sys.modules[name] = m
+        return m
+
+    stub("fbpca")
+    sk = stub("skimage")
+    sk.morphology = stub("skimage.morphology")
+    stub("boto3")
+    bc = stub("botocore")
+    bc.exceptions = stub("botocore.exceptions", ClientError=Exception)
+    cwd = os.getcwd()
+    from models import wrappers, stylegan2          # noqa: chdir side effect (models/stylegan2/__init__.py:8-16)
+    from config import Config
+    import decomposition
+    import estimators
+    os.chdir(cwd)
+    return wrappers, stylegan2, Config, decomposition, estimators
+
+
+def main():
+    wrappers, stylegan2, Config, decomposition, estimators = _import_reference()
+    sys.path.insert(0, str(REPO))
+    from oracle import ganspace_oracle as orc
+    OUT.mkdir(parents=True, exist_ok=True)
+    dev = torch.device("cpu")
+
+    class RandInitStyleGAN2(wrappers.StyleGAN2):
+        def load_model(self):                      # replaces checkpoint download (wrappers.py:153-165)
+            torch.manual_seed(1234)
+            self.model = stylegan2.Generator(self.resolution, 512, 8).to(self.device)
+            self.latent_avg = torch.zeros(512, device=self.device)
+
+    def run(cfg_kwargs, outclass, use_w):
+        m = RandInitStyleGAN2(dev, outclass)
+        inst = wrappers.get_instrumented_model("StyleGAN2", outclass, "style", dev, model=m, use_w=use_w)
+        cfg = Config(model="StyleGAN2", layer="style", output_class=outclass, estimator="ipca",
+                     use_w=use_w, **cfg_kwargs)
+        with tempfile.TemporaryDirectory() as tmp:
+            path = decomposition.get_or_compute(cfg, inst, force_recompute=True,
+                                                submit_config=SimpleNamespace(run_dir=tmp, run_dir_root=tmp))
+            with np.load(path) as data:
+                out = {k: data[k].copy() for k in data.files}
+            name = path.name
+        return out, name, m
+
+    # ---- G1: BASELINE config 1 (StyleGAN2-ffhq style --use_w, N=10k b=1k c=32) --------------------
+    out1, name1, m = run(dict(n=10_000, batch_size=1_000, components=32), "ffhq", True)
+    np.savez_compressed(OUT / "c1_stylegan2_ffhq_style_w_n10000_b1000_c32.npz", dump_name=np.array(name1), **out1)
+
+    # ---- G2: Z-space layer=style with the regression pass (config-3 shape, small N) ---------------
+    out2, name2, _ = run(dict(n=4_000, batch_size=1_000, components=16), "car", False)
+    np.savez_compressed(OUT / "c3s_stylegan2_car_style_z_n4000_b1000_c16.npz", dump_name=np.array(name2), **out2)
+
+    # ---- G3: W-space with a ragged plan (B does not divide NB; explicit seed) ----------------------
+    out3, name3, _ = run(dict(n=5_000, batch_size=700, components=20, seed=7), "ffhq", True)
+    np.savez_compressed(OUT / "w_ragged_n5000_b700_c20_seed7.npz", dump_name=np.array(name3), **out3)
+
+    # ---- G4: mapping-network known answers + sample_latent stream heads ---------------------------
+    np.random.seed(1)
+    m.use_z()
+    z = m.sample_latent(16)                         # consumes the first global seed after seed(1)
+    with torch.no_grad():
+        w = m.model.style(z)
+    heads = []
+    for s in (1791095845, 2135392491, 5, 0, 2147483646):
+        heads.append(np.random.RandomState(s).standard_normal(64).astype(np.float32))
+    tail = np.random.RandomState(1791095845).standard_normal(512 * 1000).astype(np.float32)[-64:]
+    np.random.seed(1)
+    seeds_1 = np.array([np.random.randint(np.iinfo(np.int32).max) for _ in range(16)], np.int64)
+    np.random.seed(3)
+    seeds_3 = np.array([np.random.randint(np.iinfo(np.int32).max) for _ in range(16)], np.int64)
+    sd = m.model.state_dict()
+    wsum = np.array([float(sd[f"style.{i + 1}.weight"].double().sum()) for i in range(8)])
+    np.savez_compressed(OUT / "mapping_known_answers.npz", z=z.numpy(), w=w.numpy(),
+                        head_seeds=np.array([1791095845, 2135392491, 5, 0, 2147483646], np.int64),
+                        heads=np.stack(heads), tail_1791095845_512000=tail,
+                        seeds_after_seed1=seeds_1, seeds_after_seed3=seeds_3, style_weight_sums=wsum,
+                        style1_weight_head=sd["style.1.weight"][:4, :8].numpy())
+
+    # ---- G5: IPCAEstimator chain on synthetic data (d=96, c=12, 5 batches of 300) ------------------
+    rng = np.random.RandomState(11)
+    basis = rng.standard_normal((96, 96)) * (0.9 ** np.arange(96))[None, :]
+    Xs = [(rng.standard_normal((300, 96)) @ basis.T + 3.0 * rng.standard_normal(96)).astype(np.float32)
+          for _ in range(5)]
+    est = estimators.get_estimator("ipca", 12, 1.0)
+    chain = {}
+    for k, X in enumerate(Xs):
+        assert est.fit_partial(X.copy())
+        comp, stdev, ratio = est.get_components()
+        chain[f"comp_{k}"] = np.asarray(comp, np.float64)
+        chain[f"stdev_{k}"] = np.asarray(stdev, np.float64)
+        chain[f"ratio_{k}"] = np.asarray(ratio, np.float64)
+        chain[f"mean_{k}"] = np.asarray(est.transformer.mean_, np.float64)
+        chain[f"var_{k}"] = np.asarray(est.transformer.var_, np.float64)
+        chain[f"sv_{k}"] = np.asarray(est.transformer.singular_values_, np.float64)
+    np.savez_compressed(OUT / "ipca_chain_d96_c12.npz", X=np.stack(Xs), param_str=np.array(est.get_param_str()),
+                        **chain)
+
+    # ---- report oracle-vs-reference (also asserted by tests/test_oracle_golden.py) -----------------
+    ws, bs = orc.mapping_random_init(1234)
+    for i in range(8):
+        assert np.array_equal(ws[i], sd[f"style.{i + 1}.weight"].numpy()), "mapping init mismatch"
+    print("mapping w max abs diff:", np.abs(orc.mapping_forward(z.numpy(), ws, bs) - w.numpy()).max())
+    for form in ("svd", "gram"):
+        o1 = orc.compute_stylegan2_style(ws, bs, 10_000, 1_000, 32, True, ipca=form)
+        print("G1", form, orc.compare_npz(o1, out1))
+        o2 = orc.compute_stylegan2_style(ws, bs, 4_000, 1_000, 16, False, ipca=form)
+        print("G2", form, orc.compare_npz(o2, out2))
+        o3 = orc.compute_stylegan2_style(ws, bs, 5_000, 700, 20, True, seed=7, ipca=form)
+        print("G3", form, orc.compare_npz(o3, out3))
+    print("wrote", sorted(p.name for p in OUT.glob("*.npz")))
+
+
+if __name__ == "__main__":
+    main()
