@@ -1,0 +1,387 @@
+"""ctypes binding of the C-ABI shared library (include/ganspace_b200.h).
+
+There is no CPU fallback: if the library is missing, or a compute entry point is called without a CUDA
+device, this module raises.  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "libganspace_b200.so"
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/ganspace_b200.h one to one
+_P, _I, _L, _Z, _D, _F = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double, C.c_float
+SIGNATURES = {
+    "gsb_abi_version": (_I, []),
+    "gsb_last_error": (C.c_char_p, []),
+    "gsb_legacy_normal_f32": (_I, [_P, _I, _L, _P, _L, _P]),
+    "gsb_legacy_truncnorm_f32": (_I, [_P, _I, _L, _D, _D, _F, _P, _L, _P]),
+    "gsb_mt19937_raw_u32": (_I, [_P, _I, _L, _P, _L, _P]),
+    "gsb_mapping_packed_bytes": (_Z, [_I, _I]),
+    "gsb_mapping_pack": (_I, [_P, _P, _I, _I, _F, _P, _P]),
+    "gsb_mapping_workspace_bytes": (_Z, [_L, _I]),
+    "gsb_mapping_forward": (_I, [_P, _I, _I, _P, _P, _L, _I, _P, _Z, _P]),
+    "gsb_batch_stats_workspace_bytes": (_Z, [_L, _I]),
+    "gsb_batch_stats": (_I, [_P, _L, _I, _L, _P, _P, _P, _Z, _P]),
+    "gsb_ipca_state_bytes": (_Z, [_I, _I]),
+    "gsb_ipca_workspace_bytes": (_Z, [_I, _I]),
+    "gsb_ipca_reset": (_I, [_P, _I, _I, _P]),
+    "gsb_ipca_chain_step": (_I, [_P, _I, _I, _L, _L, _P, _P, _P, _Z, _P]),
+    "gsb_ipca_export": (_I, [_P, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
+    "gsb_sym_eig_top": (_I, [_P, _I, _I, _P, _P, _P, _Z, _P]),
+    "gsb_project_std_workspace_bytes": (_Z, [_I]),
+    "gsb_project_std": (_I, [_P, _L, _I, _L, _P, _I, _P, _P, _P, _Z, _P]),
+    "gsb_linreg_state_bytes": (_Z, [_I, _I]),
+    "gsb_linreg_reset": (_I, [_P, _I, _I, _P]),
+    "gsb_linreg_workspace_bytes": (_Z, [_L, _I]),
+    "gsb_linreg_accumulate": (_I, [_P, _I, _I, _P, _L, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "gsb_linreg_solve": (_I, [_P, _I, _I, _L, _P, _P, _P]),
+}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load libganspace_b200.so (built in-tree by ``__graft_entry__.build()`` / csrc/Makefile)."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise NativeError(
+                f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). ganspace_b200 has no CPU fallback.")
+        lib = C.CDLL(str(_LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the header and the library drift apart
+            fn.restype, fn.argtypes = res, args
+        if lib.gsb_abi_version() != 1:
+            raise NativeError("ABI version mismatch between ganspace_b200/_native.py and the library")
+        _lib = lib
+    return _lib
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise NativeError("ganspace_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device(device if device is not None else "cuda")
+    if dev.type != "cuda":
+        raise NativeError(f"ganspace_b200 runs on CUDA devices only, got {dev}")
+    return dev
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "device-contiguous tensor expected"
+    return C.c_void_p(t.data_ptr())
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise NativeError(f"{what} failed ({rc}): {load().gsb_last_error().decode()}")
+
+
+class _Instrument:
+    """Launch counter and optional per-section CUDA-event timers (used by bench.py for the roofline).
+
+    ``launches`` counts the kernels this library enqueued (each C-ABI call launches a fixed number).
+    When ``timing`` is on, sections wrap their C call in a pair of events recorded on the launching
+    stream; ``section_ms()`` sums them after a synchronize."""
+
+    def __init__(self):
+        self.launches = 0
+        self.timing = False
+        self._events = {}
+
+    def reset(self):
+        self.launches = 0
+        self._events = {}
+
+    def count(self, n):
+        self.launches += n
+
+    class _Sec:
+        def __init__(self, outer, name):
+            self.o, self.name = outer, name
+
+        def __enter__(self):
+            if self.o.timing:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record(torch.cuda.current_stream())
+
+        def __exit__(self, *a):
+            if self.o.timing:
+                self.e1.record(torch.cuda.current_stream())
+                self.o._events.setdefault(self.name, []).append((self.e0, self.e1))
+
+    def section(self, name):
+        return self._Sec(self, name)
+
+    def section_ms(self):
+        torch.cuda.synchronize()
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self._events.items()}
+
+
+instrument = _Instrument()
+
+
+class _Scratch:
+    """Grow-only per-device scratch buffers keyed by purpose (the C ABI never allocates)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key, nbytes: int, device) -> torch.Tensor:
+        k = (key, str(device))
+        buf = self._bufs.get(k)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[k] = buf
+        return buf
+
+    def clear(self):
+        self._bufs.clear()
+
+
+scratch = _Scratch()
+
+
+# ------------------------------------------------------------------------------------------------
+# thin tensor-level wrappers
+# ------------------------------------------------------------------------------------------------
+def legacy_normal(seeds, n_per_stream: int, device, out=None) -> torch.Tensor:
+    """RandomState(seed).standard_normal(n_per_stream).astype(float32) for every seed -> [S, n]."""
+    lib = load()
+    dev = require_cuda(device)
+    seeds_dev = _seeds_tensor(seeds, dev)
+    S = seeds_dev.numel()
+    if out is None:
+        out = torch.empty((S, n_per_stream), dtype=torch.float32, device=dev)
+    assert out.is_cuda and out.is_contiguous() and out.numel() >= S * n_per_stream
+    with torch.cuda.device(dev), instrument.section("rng"):
+        _check(lib.gsb_legacy_normal_f32(_ptr(seeds_dev), S, n_per_stream, _ptr(out), n_per_stream, _stream()),
+               "gsb_legacy_normal_f32")
+    instrument.count(1)
+    return out
+
+
+def _seeds_tensor(seeds, dev):
+    """uint32 seeds carried in an int32 tensor (two's-complement reinterpretation)."""
+    vals = [(int(s) & 0xFFFFFFFF) for s in seeds]
+    vals = [v - (1 << 32) if v >= (1 << 31) else v for v in vals]
+    return torch.tensor(vals, dtype=torch.int32, device=dev)
+
+
+def legacy_truncnorm(seeds, n_per_stream: int, lo: float, hi: float, scale: float, device) -> torch.Tensor:
+    lib = load()
+    dev = require_cuda(device)
+    sd = _seeds_tensor(seeds, dev)
+    out = torch.empty((sd.numel(), n_per_stream), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.gsb_legacy_truncnorm_f32(_ptr(sd), sd.numel(), n_per_stream, lo, hi, scale, _ptr(out),
+                                            n_per_stream, _stream()), "gsb_legacy_truncnorm_f32")
+    return out
+
+
+def mt19937_raw(seeds, n_per_stream: int, device) -> torch.Tensor:
+    lib = load()
+    dev = require_cuda(device)
+    sd = _seeds_tensor(seeds, dev)
+    out = torch.empty((sd.numel(), n_per_stream), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.gsb_mt19937_raw_u32(_ptr(sd), sd.numel(), n_per_stream, _ptr(out), n_per_stream, _stream()),
+               "gsb_mt19937_raw_u32")
+    return out
+
+
+class PackedMapping:
+    """Pre-scaled mapping-network weights in the layout the kernels read (gsb_mapping_pack)."""
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor, lr_mul: float):
+        lib = load()
+        dev = require_cuda(weight.device)
+        self.n_layers, self.dim = int(weight.shape[0]), int(weight.shape[1])
+        assert weight.shape == (self.n_layers, self.dim, self.dim) and bias.shape == (self.n_layers, self.dim)
+        self.device = dev
+        self.packed = torch.empty(lib.gsb_mapping_packed_bytes(self.n_layers, self.dim), dtype=torch.uint8, device=dev)
+        w = weight.detach().to(dev, torch.float32).contiguous()
+        b = bias.detach().to(dev, torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            _check(lib.gsb_mapping_pack(_ptr(w), _ptr(b), self.n_layers, self.dim, float(lr_mul),
+                                        _ptr(self.packed), _stream()), "gsb_mapping_pack")
+
+    def forward(self, z: torch.Tensor, out: torch.Tensor = None, pixelnorm: bool = True,
+                force_simt: bool = False) -> torch.Tensor:
+        lib = load()
+        assert z.is_cuda and z.dtype == torch.float32 and z.shape[-1] == self.dim
+        z2 = z.reshape(-1, self.dim)
+        if not z2.is_contiguous():
+            z2 = z2.contiguous()
+        n = z2.shape[0]
+        if out is None:
+            out = torch.empty_like(z2)
+        ws_bytes = lib.gsb_mapping_workspace_bytes(n, self.dim)
+        ws = scratch.get("mapping", ws_bytes, z.device)
+        flags = (1 if pixelnorm else 0) | (2 if force_simt else 0)
+        with torch.cuda.device(z.device), instrument.section("mapping"):
+            _check(lib.gsb_mapping_forward(_ptr(self.packed), self.n_layers, self.dim, _ptr(z2), _ptr(out), n,
+                                           flags, _ptr(ws), ws.numel(), _stream()), "gsb_mapping_forward")
+        instrument.count(self.n_layers + (1 if pixelnorm else 0))
+        return out.reshape(z.shape)
+
+
+def mapping_pixelnorm(z: torch.Tensor) -> torch.Tensor:
+    """PixelNorm alone (stylegan2-pytorch/model.py:14-19)."""
+    lib = load()
+    assert z.is_cuda and z.dtype == torch.float32
+    dim = z.shape[-1]
+    z2 = z.reshape(-1, dim).contiguous()
+    out = torch.empty_like(z2)
+    ws = scratch.get("mapping", lib.gsb_mapping_workspace_bytes(z2.shape[0], dim), z.device)
+    with torch.cuda.device(z.device):
+        _check(lib.gsb_mapping_forward(C.c_void_p(0), 0, dim, _ptr(z2), _ptr(out), z2.shape[0], 1, _ptr(ws),
+                                       ws.numel(), _stream()), "gsb_mapping_forward")
+    return out.reshape(z.shape)
+
+
+def batch_stats(x: torch.Tensor, mean_out: torch.Tensor = None, gram_out: torch.Tensor = None):
+    """(mean[d] fp64, centred Gram[d,d] fp64) of x[n,d] fp32."""
+    lib = load()
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    n, d = x.shape
+    ld = x.stride(0)
+    if mean_out is None:
+        mean_out = torch.empty(d, dtype=torch.float64, device=x.device)
+    if gram_out is None:
+        gram_out = torch.empty((d, d), dtype=torch.float64, device=x.device)
+    ws_bytes = lib.gsb_batch_stats_workspace_bytes(n, d)
+    ws = scratch.get("stats", ws_bytes, x.device)
+    with torch.cuda.device(x.device), instrument.section("stats"):
+        _check(lib.gsb_batch_stats(C.c_void_p(x.data_ptr()), n, d, ld, _ptr(mean_out), _ptr(gram_out), _ptr(ws),
+                                   ws.numel(), _stream()), "gsb_batch_stats")
+    instrument.count(3)
+    return mean_out, gram_out
+
+
+class IPCAChain:
+    """Device-resident IncrementalPCA state + the Gram-form chain step (small-d engine)."""
+
+    def __init__(self, d: int, c: int, device):
+        lib = load()
+        self.dev = require_cuda(device)
+        self.d, self.c = int(d), int(c)
+        self.state = torch.empty(lib.gsb_ipca_state_bytes(self.d, self.c), dtype=torch.uint8, device=self.dev)
+        self.ws = torch.empty(lib.gsb_ipca_workspace_bytes(self.d, self.c), dtype=torch.uint8, device=self.dev)
+        self.n_seen = 0
+        with torch.cuda.device(self.dev):
+            _check(lib.gsb_ipca_reset(_ptr(self.state), self.d, self.c, _stream()), "gsb_ipca_reset")
+
+    def step(self, n_batch: int, mean_b: torch.Tensor, gram_b: torch.Tensor):
+        lib = load()
+        assert mean_b.dtype == torch.float64 and gram_b.dtype == torch.float64
+        with torch.cuda.device(self.dev), instrument.section("chain"):
+            _check(lib.gsb_ipca_chain_step(_ptr(self.state), self.d, self.c, self.n_seen, int(n_batch),
+                                           _ptr(mean_b), _ptr(gram_b), _ptr(self.ws), self.ws.numel(), _stream()),
+                   "gsb_ipca_chain_step")
+        instrument.count(7)
+        self.n_seen += int(n_batch)
+
+    def export(self):
+        lib = load()
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        out = {
+            "components": torch.empty((self.c, self.d), **f64), "singular_values": torch.empty(self.c, **f64),
+            "mean": torch.empty(self.d, **f64), "var": torch.empty(self.d, **f64),
+            "explained_variance": torch.empty(self.c, **f64),
+            "explained_variance_ratio": torch.empty(self.c, **f64),
+        }
+        with torch.cuda.device(self.dev):
+            _check(lib.gsb_ipca_export(_ptr(self.state), self.d, self.c, self.n_seen, _ptr(out["components"]),
+                                       _ptr(out["singular_values"]), _ptr(out["mean"]), _ptr(out["var"]),
+                                       _ptr(out["explained_variance"]), _ptr(out["explained_variance_ratio"]),
+                                       _stream()), "gsb_ipca_export")
+        instrument.count(1)
+        return out
+
+
+def sym_eig_top(a: torch.Tensor, c: int):
+    lib = load()
+    assert a.is_cuda and a.dtype == torch.float64 and a.dim() == 2 and a.shape[0] == a.shape[1]
+    d = a.shape[0]
+    a = a.contiguous().clone()
+    evals = torch.empty(c, dtype=torch.float64, device=a.device)
+    evecs = torch.empty((c, d), dtype=torch.float64, device=a.device)
+    ws = torch.empty(lib.gsb_ipca_workspace_bytes(d, c), dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(a.device):
+        _check(lib.gsb_sym_eig_top(_ptr(a), d, c, _ptr(evals), _ptr(evecs), _ptr(ws), ws.numel(), _stream()),
+               "gsb_sym_eig_top")
+    return evals, evecs
+
+
+def project_std(x: torch.Tensor, dirs: torch.Tensor, sub: torch.Tensor = None) -> torch.Tensor:
+    lib = load()
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    n, d = x.shape
+    dirs = dirs.to(x.device, torch.float32).contiguous()
+    c = dirs.shape[0]
+    assert dirs.shape[1] == d
+    if sub is not None:
+        sub = sub.to(x.device, torch.float64).contiguous()
+    out = torch.empty(c, dtype=torch.float32, device=x.device)
+    ws = scratch.get("projstd", lib.gsb_project_std_workspace_bytes(c), x.device)
+    with torch.cuda.device(x.device):
+        _check(lib.gsb_project_std(C.c_void_p(x.data_ptr()), n, d, x.stride(0), _ptr(dirs), c, _ptr(sub), _ptr(out),
+                                   _ptr(ws), ws.numel(), _stream()), "gsb_project_std")
+    instrument.count(2)
+    return out
+
+
+class LinregAccumulator:
+    """Normal-equation accumulators of the latent regression (decomposition.py:77-139)."""
+
+    def __init__(self, c: int, latent_dim: int, device):
+        lib = load()
+        self.dev = require_cuda(device)
+        self.c, self.L = int(c), int(latent_dim)
+        self.state = torch.empty(lib.gsb_linreg_state_bytes(self.c, self.L), dtype=torch.uint8, device=self.dev)
+        self.n_total = 0
+        with torch.cuda.device(self.dev):
+            _check(lib.gsb_linreg_reset(_ptr(self.state), self.c, self.L, _stream()), "gsb_linreg_reset")
+
+    def accumulate(self, act, comp32, mean32, stdev32, z):
+        lib = load()
+        n, d = act.shape
+        act, comp32, mean32, stdev32, z = (t.contiguous() for t in (act, comp32, mean32, stdev32, z))
+        assert z.shape == (n, self.L) and comp32.shape == (self.c, d)
+        ws = scratch.get("linreg", lib.gsb_linreg_workspace_bytes(n, self.c), self.dev)
+        with torch.cuda.device(self.dev):
+            _check(lib.gsb_linreg_accumulate(_ptr(self.state), self.c, self.L, _ptr(act), n, d, _ptr(comp32),
+                                             _ptr(mean32), _ptr(stdev32), _ptr(z), _ptr(ws), ws.numel(), _stream()),
+                   "gsb_linreg_accumulate")
+        instrument.count(2)
+        self.n_total += n
+
+    def solve(self):
+        lib = load()
+        M = torch.empty((self.c, self.L), dtype=torch.float64, device=self.dev)
+        zmean = torch.empty(self.L, dtype=torch.float64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _check(lib.gsb_linreg_solve(_ptr(self.state), self.c, self.L, self.n_total, _ptr(M), _ptr(zmean), _stream()),
+                   "gsb_linreg_solve")
+        instrument.count(1)
+        return M, zmean

@@ -1,0 +1,339 @@
+"""Decomposition driver: ``get_or_compute`` / ``compute`` -- the hot path's public entry point.
+
+Mirror of /root/reference/decomposition.py (get_or_compute :362-368, _compute :370-402, compute :150-358,
+linreg_lstsq :77-139, get_random_dirs :42-46, get_max_batch_size :49-74): same signature, validation
+errors, cache-file naming, seeding protocol and 8-array ``.npz`` schema, so ``visualize.py``,
+``interactive.py`` and the notebooks consume the result unchanged.
+
+What changed is where the work happens.  The reference samples latents on the host, round-trips every
+batch through host memory and runs sklearn's IncrementalPCA on the CPU; here
+  * every NumPy-legacy latent stream of the run is generated on the GPU (one CTA per sample_latent seed),
+  * the mapping network / hooked layer runs in hand-written CUDA kernels,
+  * the IncrementalPCA merge chain runs on the device from per-group (mean, centred Gram) statistics,
+  * the regression pass accumulates normal equations on the device,
+so activations never leave HBM; the host only draws the seeds (NumPy global state, as the reference
+does) and receives the final components.
+
+Multi-GPU (one process per GPU, torch.distributed initialised): partial_fit group k is owned by rank
+k mod world; every rank computes the statistics of its groups into slot k of a [K, d*d+d] buffer, ONE
+all-reduce exchanges them, and every rank replays the K-step chain in the reference's order -- the
+result does not depend on the world size.
+"""
+from __future__ import annotations
+
+import datetime
+import os
+import sys
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _native
+from . import plan as _plan
+from .config import Config  # noqa: F401  (re-exported like the reference module does)
+from .estimators import get_estimator
+from .models import get_instrumented_model
+from .netdissect.nethook import InstrumentedModel
+
+SEED_SAMPLING = 1
+SEED_RANDOM_DIRS = 2
+SEED_LINREG = 3
+SEED_VISUALIZATION = 5
+
+B = 20
+n_clusters = 500
+
+# bytes of latents generated per pipeline chunk (HBM is 180 GB; 8 GiB keeps config 2 in one chunk)
+LATENT_CHUNK_BYTES = 8 << 30
+
+
+def get_random_dirs(components, dimensions):
+    gen = np.random.RandomState(seed=SEED_RANDOM_DIRS)
+    dirs = gen.normal(size=(components, dimensions))
+    dirs /= np.sqrt(np.sum(dirs ** 2, axis=1, keepdims=True))
+    return dirs.astype(np.float32)
+
+
+def get_max_batch_size(inst, device, layer_name=None):
+    """Largest probe batch (<= 20) whose peak memory stays under half the device (reference :49-74)."""
+    inst.remove_edits()
+    torch.cuda.reset_peak_memory_stats(device)
+    total_mem = torch.cuda.get_device_properties(device).total_memory
+    B_max = 20
+    for i in range(2, B_max, 2):
+        z = inst.model.sample_latent(n_samples=i)
+        if layer_name:
+            inst.model.partial_forward(z, layer_name)
+        else:
+            inst.model.forward(z)
+        maxmem = torch.cuda.max_memory_allocated(device)
+        del z
+        if maxmem > 0.5 * total_mem:
+            print("Batch size {:d}: memory usage {:.0f}MB".format(i, maxmem / 1e6))
+            return i
+    return B_max
+
+
+def _dist():
+    """(rank, world, group-is-live) of the data-parallel job, (0, 1, False) when not distributed."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size(), True
+    return 0, 1, False
+
+
+def _draw_seeds(count):
+    """``count`` successive ``np.random.randint(int32 max)`` draws on the global state, i.e. the seeds that
+    ``count`` successive ``sample_latent()`` calls would consume (models/wrappers.py:168-169)."""
+    hi = np.iinfo(np.int32).max
+    return [int(np.random.randint(hi)) for _ in range(count)]
+
+
+def _sample_batches(model, Bsz, seeds, out=None):
+    """Rows of len(seeds) consecutive ``sample_latent(Bsz)`` calls, as one [len*Bsz, ...] device tensor."""
+    if hasattr(model, "sample_latents_multi"):
+        return model.sample_latents_multi(Bsz, seeds, out=out)
+    return torch.cat([model.sample_latent(Bsz, seed=s) for s in seeds], dim=0)
+
+
+# Solve for directions in latent space that match PCs in activation space (reference :77-139)
+def linreg_lstsq(comp_np, mean_np, stdev_np, inst, config):
+    print("Performing least squares regression", flush=True)
+    torch.manual_seed(SEED_LINREG)
+    np.random.seed(SEED_LINREG)
+    model = inst.model
+    dev = model.device
+    comp = torch.from_numpy(comp_np).float().to(dev).contiguous()
+    mean = torch.from_numpy(mean_np).float().to(dev).reshape(-1).contiguous()
+    stdev = torch.from_numpy(stdev_np).float().to(dev).contiguous()
+
+    n_samp = max(10_000, config.n) // B * B
+    n_comp = comp.shape[0]
+    latent_dims = int(model.get_latent_dims())      # consumes one global draw, as in the reference (:88)
+    rank, world, live = _dist()
+
+    acc = _native.LinregAccumulator(n_comp, latent_dims, dev)
+    seeds = _draw_seeds(n_samp // B)
+    group = max(1, min(len(seeds), (256 << 20) // max(1, B * latent_dims * 4)))
+    for start in range(0, len(seeds), group):
+        idx = [i for i in range(start, min(start + group, len(seeds))) if i % world == rank]
+        if not idx:
+            continue
+        z_all = _sample_batches(model, B, [seeds[i] for i in idx])
+        for j in range(len(idx)):
+            z = z_all[j * B:(j + 1) * B]
+            with torch.no_grad():
+                model.partial_forward(z, config.layer)
+            act = inst.retained_features()[config.layer].reshape(B, -1)
+            acc.accumulate(act.contiguous(), comp, mean, stdev, z.reshape(B, -1).contiguous())
+    if live:
+        import torch.distributed as dist
+        flat = acc.state.view(torch.float64)
+        dist.all_reduce(flat)
+    acc.n_total = n_samp
+    M_t, Z_mean = acc.solve()
+    return M_t.cpu().numpy()[:n_comp, :], Z_mean.cpu().numpy().reshape(1, -1)
+
+
+def regression(comp, mean, stdev, inst, config):
+    M = np.dot(comp, comp.T)
+    if not np.allclose(M, np.identity(M.shape[0])):
+        det = np.linalg.det(M)
+        print(f"WARNING: Computed basis is not orthonormal (determinant={det})")
+    return linreg_lstsq(comp, mean, stdev, inst, config)
+
+
+def compute(config, dump_name, instrumented_model):
+    """decomposition.compute (:150-358): run the pipeline, rank 0 writes the 8-array .npz."""
+    timestamp = lambda: datetime.datetime.now().strftime("%d.%m %H:%M")
+    print(f"[{timestamp()}] Computing", dump_name.name)
+    arrays = compute_arrays(config, instrumented_model)
+    rank, world, live = _dist()
+    if rank == 0:
+        os.makedirs(dump_name.parent, exist_ok=True)
+        np.savez_compressed(dump_name, **arrays)
+    if live:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def compute_arrays(config, instrumented_model):
+    """Everything of compute() up to (not including) the file write; returns the 8 float32 arrays."""
+    global B
+
+    torch.manual_seed(0)
+    np.random.seed(0)
+
+    device = _native.require_cuda("cuda")      # no CPU fallback (the reference falls back to 'cpu', :163-164)
+    rank, world, live = _dist()
+    layer_key = config.layer
+
+    if instrumented_model is None:
+        inst = get_instrumented_model(config.model, config.output_class, layer_key,
+                                      torch.device("cuda", torch.cuda.current_device()))
+        model = inst.model
+    else:
+        print("Reusing InstrumentedModel instance")
+        inst = instrumented_model
+        model = inst.model
+        inst.remove_edits()
+        model.set_output_class(config.output_class)
+    device = model.device
+
+    if config.use_w:
+        print("Using W latent space")
+        model.use_w()
+
+    inst.retain_layer(layer_key)
+    model.partial_forward(model.sample_latent(1), layer_key)
+    sample_shape = inst.retained_features()[layer_key].shape
+    sample_dims = int(np.prod(sample_shape))
+    print("Feature shape:", sample_shape)
+
+    input_shape = inst.model.get_latent_shape()
+    input_dims = int(inst.model.get_latent_dims())
+
+    config.components = min(config.components, sample_dims)
+    transformer = get_estimator(config.estimator, config.components, config.sparsity, device=device)
+    if not transformer.batch_support:
+        raise RuntimeError("only batched estimators run on the device path")
+
+    B = config.batch_size or get_max_batch_size(inst, device, layer_key)
+    pl = _plan.make_plan(config.n, B, config.components)
+    N, NB = pl.N, pl.NB
+    print("B={}, N={}, dims={}, N/dims={:.1f}".format(B, N, sample_dims, N / sample_dims), flush=True)
+
+    torch.manual_seed(config.seed or SEED_SAMPLING)
+    np.random.seed(config.seed or SEED_SAMPLING)
+
+    # ---- Phase A: the seeds of every sample_latent(B) call the reference makes (:232-236) ----------
+    seeds = _draw_seeds(pl.n_calls)
+    samples_are_latents = layer_key in ["g_mapping", "style"] and inst.model.latent_space_name() == "W"
+
+    # ---- Phase B: per-group statistics + merge chain (:239-265) ------------------------------------
+    K = pl.K
+    d = sample_dims
+    groups_per_chunk = max(1, int(LATENT_CHUNK_BYTES // max(1, NB * input_dims * 4)))
+    slots = torch.zeros((K, _plan.slot_width(d)), dtype=torch.float64, device=device) if live else None
+    X = None
+    tr = transformer.transformer
+    for c0 in range(0, K, groups_per_chunk):
+        mine = _plan.groups_to_process(pl, rank, world, c0, min(c0 + groups_per_chunk, K))
+        for run in _plan.contiguous_runs(mine):          # contiguous groups share generated batches
+            row0, row1 = pl.group_rows(run[0])[0], pl.group_rows(run[-1])[1]
+            b0, b1 = pl.batches_covering(row0, row1)
+            lat = _sample_batches(model, B, seeds[b0:b1])
+            lat = lat.reshape(lat.shape[0], -1)
+            for k in run:
+                gi = pl.group_rows(k)[0]
+                rows = lat[gi - b0 * B: gi - b0 * B + NB]
+                if samples_are_latents:
+                    X = rows
+                else:
+                    X = torch.empty((NB, d), dtype=torch.float32, device=device)
+                    for mb in range(0, NB, B):
+                        z = rows[mb:mb + B].reshape(-1, *input_shape[1:])
+                        with torch.no_grad():
+                            model.partial_forward(z, layer_key)
+                        batch = inst.retained_features()[layer_key].reshape((z.shape[0], -1))
+                        space_left = min(B, NB - mb)
+                        X[mb:mb + space_left] = batch[:space_left]
+                if live:
+                    if _plan.owner(k, world) == rank:
+                        n_b, mean_b, gram_b = tr.batch_stats(X)
+                        slots[k, :d * d] = gram_b.reshape(-1)
+                        slots[k, d * d:] = mean_b
+                elif not transformer.fit_partial(X):
+                    break
+            del lat    # X (a view of the last group when samples_are_latents) keeps its storage alive
+    if live:
+        import torch.distributed as dist
+        dist.all_reduce(slots)                         # the run's single exchange of PCA statistics
+        _plan.replay(pl, slots, d, lambda nb, m, g: tr.merge(nb, m.contiguous(), g.contiguous()))
+
+    X_global_mean = tr.mean_.reshape((1, sample_dims))
+    X_comp, X_stdev, X_var_ratio = transformer.get_components()
+    X_comp = np.array(X_comp, copy=True)
+
+    assert X_comp.shape[1] == sample_dims and X_comp.shape[0] == config.components \
+        and X_global_mean.shape[1] == sample_dims and X_stdev.shape[0] == config.components, "Invalid shape"
+
+    if samples_are_latents:
+        Z_comp = X_comp
+        Z_global_mean = X_global_mean
+    else:
+        Z_comp, Z_global_mean = regression(X_comp, X_global_mean, X_stdev, inst, config)
+
+    Z_comp /= np.linalg.norm(Z_comp, axis=-1, keepdims=True)
+
+    # random projections of the last group's buffer, centred on the global mean (:289-291,312-316)
+    random_dirs = get_random_dirs(config.components, int(np.prod(sample_shape)))
+    n_rand_samples = min(5000, X.shape[0])
+    mean_dev = tr.device_attributes()["mean"]
+    X_stdev_random = _native.project_std(X[:n_rand_samples], torch.from_numpy(random_dirs), sub=mean_dev).cpu().numpy()
+
+    X_comp = X_comp.reshape(-1, *sample_shape)
+    X_global_mean = X_global_mean.reshape(sample_shape)
+    Z_comp = Z_comp.reshape(-1, *input_shape)
+    Z_global_mean = Z_global_mean.reshape(input_shape)
+
+    lat_stdev = np.ones_like(X_stdev)
+    if config.use_w:
+        samples = model.sample_latent(5000).reshape(5000, input_dims)
+        zc = torch.from_numpy(Z_comp.reshape(-1, input_dims).astype(np.float32))
+        lat_stdev = _native.project_std(samples.contiguous(), zc).cpu().numpy()
+
+    arrays = {
+        "act_comp": X_comp.astype(np.float32),
+        "act_mean": X_global_mean.astype(np.float32),
+        "act_stdev": X_stdev.astype(np.float32),
+        "lat_comp": Z_comp.astype(np.float32),
+        "lat_mean": Z_global_mean.astype(np.float32),
+        "lat_stdev": lat_stdev.astype(np.float32),
+        "var_ratio": X_var_ratio.astype(np.float32),
+        "random_stdevs": X_stdev_random.astype(np.float32),
+    }
+    if instrumented_model is None:
+        inst.close()
+        del inst
+        del model
+    return arrays
+
+
+def get_or_compute(config, model=None, submit_config=None, force_recompute=False):
+    if submit_config is None:
+        wrkdir = str(Path(__file__).parent.resolve())
+        submit_config = SimpleNamespace(run_dir_root=wrkdir, run_dir=wrkdir)
+    return _compute(submit_config, config, model, force_recompute)
+
+
+def _compute(submit_config, config, model=None, force_recompute=False):
+    basedir = Path(submit_config.run_dir)
+
+    if config.n is None:
+        raise RuntimeError("Must specify number of samples with -n=XXX")
+    if model and not isinstance(model, InstrumentedModel):
+        raise RuntimeError('Passed model has to be wrapped in "InstrumentedModel"')
+    if config.use_w and "StyleGAN" not in config.model:
+        raise RuntimeError(f"Cannot change latent space of non-StyleGAN model {config.model}")
+
+    transformer = get_estimator(config.estimator, config.components, config.sparsity)
+    dump_name = "{}-{}_{}_{}_n{}{}{}.npz".format(
+        config.model.lower(),
+        config.output_class.replace(" ", "_"),
+        config.layer.lower(),
+        transformer.get_param_str(),
+        config.n,
+        "_w" if config.use_w else "",
+        f"_seed{config.seed}" if config.seed else "",
+    )
+    dump_path = basedir / "cache" / "components" / dump_name
+
+    if not dump_path.is_file() or force_recompute:
+        print("Not cached")
+        t_start = datetime.datetime.now()
+        compute(config, dump_path, model)
+        print("Total time:", datetime.datetime.now() - t_start)
+    return dump_path

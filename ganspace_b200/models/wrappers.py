@@ -1,0 +1,272 @@
+"""Model wrappers of the hot path: ``BaseModel``, ``StyleGAN2``, ``get_model``, ``get_instrumented_model``.
+
+Mirror of /root/reference/models/wrappers.py (BaseModel :27-94, StyleGAN2 :97-267, factories :651-735):
+same class and method names, argument meaning and error behaviour, so ``decomposition.get_or_compute``,
+``visualize.py`` and the notebooks call them unchanged.  Differences, all on the device side:
+
+* ``sample_latent`` draws the NumPy-legacy normal stream ON THE GPU (bit-exact MT19937 + polar method,
+  csrc/rng.cu) -- the seed is still taken from NumPy's global state on the host exactly as the reference
+  does (wrappers.py:168-169), so seeds and latents are identical.
+* ``Generator.style`` runs the hand-written mapping kernels (csrc/mapping*.cu).
+* ``partial_forward(x, 'style')`` stops right after the mapping network; the reference first builds the
+  ``[B, n_latent, 512]`` repeat+stack that the early exit then throws away (wrappers.py:202-222).
+* checkpoints: no network here.  A rosinality ``g_ema`` checkpoint under $GANCONTROL_CHECKPOINT_DIR is
+  loaded when present; otherwise ``random_init=<seed>`` (or env GANSPACE_B200_RANDOM_INIT) reproduces the
+  reference's default initialisation under ``torch.manual_seed(seed)`` (the BASELINE.json configs).
+"""
+from __future__ import annotations
+
+import os
+from abc import ABC as AbstractBaseClass, abstractmethod
+from functools import singledispatch
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from .. import _native
+from ..config import Config
+from ..netdissect.nethook import InstrumentedModel
+from . import stylegan2
+
+INT32_MAX = int(np.iinfo(np.int32).max)
+
+
+def _global_seed() -> int:
+    """``np.random.randint(np.iinfo(np.int32).max)`` on NumPy's global legacy state (wrappers.py:169)."""
+    return int(np.random.randint(INT32_MAX))
+
+
+class BaseModel(AbstractBaseClass, torch.nn.Module):
+    def __init__(self, model_name, class_name):
+        super().__init__()
+        self.model_name = model_name
+        self.outclass = class_name
+
+    @abstractmethod
+    def partial_forward(self, x, layer_name):
+        """Run the network only up to ``layer_name`` (hooks fire as a side effect); returns None."""
+
+    @abstractmethod
+    def sample_latent(self, n_samples=1, seed=None, truncation=None):
+        """Batch of latents on ``self.device``."""
+
+    def get_max_latents(self):
+        return 1
+
+    def latent_space_name(self):
+        return "Z"
+
+    def get_latent_shape(self):
+        return tuple(self.sample_latent(1).shape)
+
+    def get_latent_dims(self):
+        return np.prod(self.get_latent_shape())
+
+    def set_output_class(self, new_class):
+        self.outclass = new_class
+
+    def forward(self, x):
+        out = self.model.forward(x)
+        return 0.5 * (out + 1)
+
+    def sample_np(self, z=None, n_samples=1, seed=None):
+        if z is None:
+            z = self.sample_latent(n_samples, seed=seed)
+        elif isinstance(z, list):
+            z = [torch.tensor(l).to(self.device) if not torch.is_tensor(l) else l for l in z]
+        elif not torch.is_tensor(z):
+            z = torch.tensor(z).to(self.device)
+        img = self.forward(z)
+        img_np = img.permute(0, 2, 3, 1).cpu().detach().numpy()
+        return np.clip(img_np, 0.0, 1.0).squeeze()
+
+    def get_conditional_state(self, z):
+        return None
+
+    def set_conditional_state(self, z, c):
+        return z
+
+    def named_modules(self, *args, **kwargs):
+        return self.model.named_modules(*args, **kwargs)
+
+
+class StyleGAN2(BaseModel):
+    CONFIGS = {"ffhq": 1024, "car": 512, "cat": 256, "church": 256, "horse": 256,
+               "bedrooms": 256, "kitchen": 256, "places": 256}
+
+    def __init__(self, device, class_name, truncation=1.0, use_w=False, random_init=None):
+        super().__init__("StyleGAN2", class_name or "ffhq")
+        self.device = _native.require_cuda(device)
+        self.truncation = truncation
+        self.latent_avg = None
+        self.w_primary = use_w
+        assert self.outclass in self.CONFIGS, \
+            f'Invalid StyleGAN2 class {self.outclass}, should be one of [{", ".join(self.CONFIGS.keys())}]'
+        self.resolution = self.CONFIGS[self.outclass]
+        self.name = f"StyleGAN2-{self.outclass}"
+        self.has_latent_residual = True
+        self._random_init = random_init
+        self.load_model()
+        self.set_noise_seed(0)
+
+    def latent_space_name(self):
+        return "W" if self.w_primary else "Z"
+
+    def use_w(self):
+        self.w_primary = True
+
+    def use_z(self):
+        self.w_primary = False
+
+    def load_model(self):
+        root = os.environ.get("GANCONTROL_CHECKPOINT_DIR", Path(__file__).parent / "checkpoints")
+        checkpoint = Path(root) / f"stylegan2/stylegan2_{self.outclass}_{self.resolution}.pt"
+        seed = self._random_init
+        if seed is None and os.environ.get("GANSPACE_B200_RANDOM_INIT"):
+            seed = int(os.environ["GANSPACE_B200_RANDOM_INIT"])
+        if checkpoint.is_file() and seed is None:
+            self.model = stylegan2.Generator(self.resolution, 512, 8)
+            ckpt = torch.load(checkpoint, map_location="cpu")
+            self.model.load_state_dict(ckpt["g_ema"], strict=False)
+            self.model = self.model.to(self.device)
+            self.latent_avg = ckpt["latent_avg"].to(self.device)
+        elif seed is not None:
+            # the reference's default init, bit-for-bit: parameters are created on the host in the
+            # reference's order under one manual seed, then moved to the device
+            torch.manual_seed(int(seed))
+            self.model = stylegan2.Generator(self.resolution, 512, 8).to(self.device)
+            self.latent_avg = torch.zeros(512, device=self.device)
+        else:
+            raise RuntimeError(
+                f"StyleGAN2 checkpoint {checkpoint} not found and no network access to download it; pass "
+                "random_init=<seed> (or set GANSPACE_B200_RANDOM_INIT) for random-init weights")
+
+    def sample_latent(self, n_samples=1, seed=None, truncation=None):
+        if seed is None:
+            seed = _global_seed()
+        z = _native.legacy_normal([seed], 512 * n_samples, self.device).view(n_samples, 512)
+        if self.w_primary:
+            z = self.model.style(z)
+        return z
+
+    def sample_latents_multi(self, n_samples, seeds, out=None):
+        """Several ``sample_latent(n_samples, seed=s)`` calls in ONE launch (one CTA per seed);
+        ``out`` is an optional [len(seeds)*n_samples, 512] device buffer.  Used by the decomposition
+        driver so that a whole run's ~100 independent streams fill the machine."""
+        S = len(seeds)
+        z = _native.legacy_normal(list(seeds), 512 * n_samples, self.device,
+                                  out=None if out is None else out.view(S, 512 * n_samples))
+        z = z.view(S * n_samples, 512)
+        if self.w_primary:
+            z = self.model.style(z) if out is None else self.model.style.packed().forward(z, out=z)
+        return z
+
+    def get_max_latents(self):
+        return self.model.n_latent
+
+    def set_output_class(self, new_class):
+        if self.outclass != new_class:
+            raise RuntimeError("StyleGAN2: cannot change output class without reloading")
+
+    def forward(self, x):
+        x = x if isinstance(x, list) else [x]
+        out, _ = self.model(x, noise=self.noise, truncation=self.truncation,
+                            truncation_latent=self.latent_avg, input_is_w=self.w_primary)
+        return 0.5 * (out + 1)
+
+    def partial_forward(self, x, layer_name):
+        styles = x if isinstance(x, list) else [x]
+        if not self.w_primary:
+            styles = [self.model.style(s) for s in styles]
+        if "style" in layer_name:
+            return
+        raise NotImplementedError(
+            f"StyleGAN2.partial_forward to layer '{layer_name}': the synthesis blocks (SURVEY.md section 8 row a5) "
+            "are not built in this round; there is no PyTorch fallback")
+
+    def set_noise_seed(self, seed):
+        # same generator stream as the reference (torch.manual_seed(seed); torch.randn per noise map),
+        # drawn on the host so that it does not depend on the device RNG implementation
+        torch.manual_seed(seed)
+        self.noise = [torch.randn(1, 1, 2 ** 2, 2 ** 2).to(self.device)]
+        for i in range(3, self.model.log_size + 1):
+            for _ in range(2):
+                self.noise.append(torch.randn(1, 1, 2 ** i, 2 ** i).to(self.device))
+
+
+# ---- factories (wrappers.py:651-735) ---------------------------------------------------------------
+@singledispatch
+def get_model(name, output_class, device, **kwargs):
+    inst = kwargs.get("inst", None)
+    model = kwargs.get("model", None)
+    if inst or model:
+        cached = model or inst.model
+        network_same = cached.model_name == name
+        outclass_same = cached.outclass == output_class
+        can_change_class = "BigGAN" in name
+        if network_same and (outclass_same or can_change_class):
+            cached.set_output_class(output_class)
+            return cached
+    if name == "StyleGAN2":
+        model = StyleGAN2(device, class_name=output_class, random_init=kwargs.get("random_init"))
+    elif "BigGAN" in name:
+        assert "-" in name, "Please specify BigGAN resolution, e.g. BigGAN-512"
+        from .biggan import BigGAN
+        model = BigGAN(device, name.split("-")[-1], class_name=output_class, random_init=kwargs.get("random_init"))
+    elif name in ("StyleGAN", "ProGAN", "DCGAN"):
+        raise RuntimeError(f"{name} is outside the B200 hot path (SURVEY.md section 2: not in any BASELINE config)")
+    else:
+        raise RuntimeError(f"Unknown model {name}")
+    return model
+
+
+@get_model.register(Config)
+def _(cfg, device, **kwargs):
+    kwargs["use_w"] = kwargs.get("use_w", cfg.use_w)
+    return get_model(cfg.model, cfg.output_class, device, **kwargs)
+
+
+def _annotate_shapes(inst, model, layers):
+    """The reference runs one full forward on zeros to record shapes (modelconfig.py:110-144).  Only the
+    hooked layers' shapes and the latent shape are consumed by GANSpace, so a partial forward suffices."""
+    input_shape = model.get_latent_shape()
+    inst.retain_layers(layers)
+    with torch.no_grad():
+        dry = torch.zeros(input_shape, device=model.device)
+        for layer in layers:
+            model.partial_forward(dry, layer)
+    inst.input_shape = input_shape
+    inst.feature_shape = {layer: feat.shape for layer, feat in inst.retained_features().items()}
+    inst.output_shape = None   # full image synthesis: SURVEY.md section 8(f) item 2
+    return inst
+
+
+@singledispatch
+def get_instrumented_model(name, output_class, layers, device, **kwargs):
+    model = get_model(name, output_class, device, **kwargs)
+    model.eval()
+    inst = kwargs.get("inst", None)
+    if inst:
+        inst.close()
+    if not isinstance(layers, list):
+        layers = [layers]
+    module_names = [n for (n, _) in model.named_modules()]
+    for layer_name in layers:
+        if layer_name not in module_names:
+            print(f"Layer '{layer_name}' not found in model!")
+            print("Available layers:", "\n".join(module_names))
+            raise RuntimeError(f"Unknown layer '{layer_name}''")
+    if hasattr(model, "use_z"):
+        model.use_z()
+    inst = _annotate_shapes(InstrumentedModel(model), model, layers)
+    if kwargs.get("use_w", False):
+        model.use_w()
+    return inst
+
+
+@get_instrumented_model.register(Config)
+def _(cfg, device, **kwargs):
+    kwargs["use_w"] = kwargs.get("use_w", cfg.use_w)
+    return get_instrumented_model(cfg.model, cfg.output_class, cfg.layer, device, **kwargs)

@@ -1,0 +1,70 @@
+"""Host-side batch plan of decomposition.compute and its data-parallel sharding (pure Python, no device).
+
+Restates the reference's sizing rules (decomposition.py:198-232) and defines how the partial_fit groups
+are distributed over ranks: group k -> rank k mod world, statistics exchanged through
+slot k of a [K, d*d+d] buffer with ONE all-reduce, chain replayed in order by every rank.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Sequence
+
+
+@dataclass(frozen=True)
+class Plan:
+    B: int          # rows per sample_latent() call
+    N: int          # samples entering the PCA  (n // B * B,               decomposition.py:201)
+    NB: int         # rows per partial_fit      (max(B, 2000, 3c),         decomposition.py:220)
+    n_lat: int      # latents drawn in phase A  (((N+NB-1)//B+1)*B,        decomposition.py:232)
+    K: int          # number of partial_fit groups (range(0, N, NB),       decomposition.py:245)
+
+    @property
+    def n_calls(self) -> int:
+        return self.n_lat // self.B
+
+    def group_rows(self, k: int):
+        return k * self.NB, k * self.NB + self.NB
+
+    def batches_covering(self, row0: int, row1: int):
+        """sample_latent call indices [b0, b1) whose rows cover [row0, row1)."""
+        return row0 // self.B, (row1 + self.B - 1) // self.B
+
+
+def make_plan(n: int, B: int, components: int) -> Plan:
+    N = n // B * B
+    NB = max(B, max(2_000, 3 * components))
+    n_lat = ((N + NB - 1) // B + 1) * B
+    K = len(range(0, N, NB))
+    return Plan(B=B, N=N, NB=NB, n_lat=n_lat, K=K)
+
+
+def owner(k: int, world: int) -> int:
+    return k % world
+
+
+def groups_to_process(plan: Plan, rank: int, world: int, first: int = 0, last: int = None) -> List[int]:
+    """Groups a rank touches in [first, last): the ones it owns, plus the final group on every rank (its
+    sample buffer feeds random_stdevs, decomposition.py:313-316)."""
+    last = plan.K if last is None else last
+    return [k for k in range(first, last) if owner(k, world) == rank or k == plan.K - 1]
+
+
+def contiguous_runs(ks: Sequence[int]) -> List[List[int]]:
+    runs: List[List[int]] = []
+    for k in ks:
+        if runs and k == runs[-1][-1] + 1:
+            runs[-1].append(k)
+        else:
+            runs.append([k])
+    return runs
+
+
+def slot_width(d: int) -> int:
+    """doubles per statistics slot: centred Gram [d*d] followed by the batch mean [d]."""
+    return d * d + d
+
+
+def replay(plan: Plan, slots, d: int, merge: Callable):
+    """Replay the K-step chain from the exchanged statistics, in the reference's group order."""
+    for k in range(plan.K):
+        merge(plan.NB, slots[k, d * d:], slots[k, :d * d].reshape(d, d))

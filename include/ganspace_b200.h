@@ -1,0 +1,150 @@
+/*
+ * ganspace_b200 -- C ABI of the B200-native activation-sampling + incremental-PCA hot path.
+ *
+ * The reference (harskish/ganspace) has NO C ABI / FFI on this path: its boundary is three duck-typed
+ * Python surfaces.  This header is the drop-in boundary the Python host mirror
+ * (ganspace_b200/*.py) binds with ctypes; each entry point cites the reference code it replaces
+ * (paths relative to /root/reference).  The binding a reference maintainer would add is shown in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `d_` pointers are CUDA device pointers, `h_` host pointers
+ *   - every call is enqueued on `stream` (a cudaStream_t passed as void*), never synchronises, never
+ *     allocates: the caller passes a workspace sized by the matching *_workspace_bytes() query
+ *   - return 0 on success, <0 on error; gsb_last_error() returns a thread-local message
+ *   - not thread-safe on one state/workspace; re-entrant across distinct ones
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns GSB_ERR_CUDA
+ */
+#ifndef GANSPACE_B200_H
+#define GANSPACE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB_ABI_VERSION 1
+
+#define GSB_OK 0
+#define GSB_ERR_ARG (-1)      /* bad argument (shape, alignment, null pointer) */
+#define GSB_ERR_CUDA (-2)     /* CUDA runtime error (message in gsb_last_error) */
+#define GSB_ERR_WORKSPACE (-3) /* workspace too small */
+
+typedef void *gsb_stream_t; /* cudaStream_t */
+
+int gsb_abi_version(void);
+const char *gsb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Latent sampling: NumPy legacy RandomState streams, bit-exact, one independent stream per seed.
+ *   replaces  models/wrappers.py:167-175  StyleGAN2.sample_latent:
+ *       rng = np.random.RandomState(seed); rng.standard_normal(512*n).reshape(n,512) -> .float()
+ *   (MT19937 init_genrand seeding, 53-bit doubles, Marsaglia polar pair emitted as [f*x2, f*x1],
+ *    cast to float32).  Stream s writes n_per_stream floats at d_out + s*out_stride.
+ * ---------------------------------------------------------------------------------------------- */
+int gsb_legacy_normal_f32(const uint32_t *d_seeds, int n_streams, int64_t n_per_stream,
+                          float *d_out, int64_t out_stride, gsb_stream_t stream);
+
+/*   replaces  models/biggan/pytorch_biggan/pytorch_pretrained_biggan/utils.py:21-33
+ *       truncnorm.rvs(-2, 2, size=(B,128), random_state=RandomState(seed)).astype(f32) * truncation
+ *   (SciPy draws RandomState.uniform and applies the inverse CDF: ndtri(Phi(a) + u*(Phi(b)-Phi(a)))). */
+int gsb_legacy_truncnorm_f32(const uint32_t *d_seeds, int n_streams, int64_t n_per_stream,
+                             double lo, double hi, float scale,
+                             float *d_out, int64_t out_stride, gsb_stream_t stream);
+
+/* raw tempered MT19937 outputs (test hook for bit-exactness of the generator itself) */
+int gsb_mt19937_raw_u32(const uint32_t *d_seeds, int n_streams, int64_t n_per_stream,
+                        uint32_t *d_out, int64_t out_stride, gsb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * StyleGAN2 mapping network  z[n,dim] -> w[n,dim]
+ *   replaces  models/stylegan2/stylegan2-pytorch/model.py:400-409 (Generator.style =
+ *             PixelNorm + n_layers x EqualLinear(dim,dim,lr_mul,activation='fused_lrelu')),
+ *             model.py:14-19 (PixelNorm), :151-161 (EqualLinear.forward),
+ *             op/fused_act.py:86-92 / op/fused_bias_act_kernel.cu:19-49 (bias + leaky-ReLU 0.2 * sqrt2)
+ *   gsb_mapping_pack pre-multiplies weight*scale (scale = lr_mul/sqrt(dim)) and bias*lr_mul once
+ *   (the reference re-materialises them on every call, model.py:153) and lays the weights out for
+ *   the kernels.  d_weight: [n_layers, dim(out), dim(in)] float32, d_bias: [n_layers, dim].
+ * ---------------------------------------------------------------------------------------------- */
+size_t gsb_mapping_packed_bytes(int n_layers, int dim);
+int gsb_mapping_pack(const float *d_weight, const float *d_bias, int n_layers, int dim, float lr_mul,
+                     void *d_packed, gsb_stream_t stream);
+size_t gsb_mapping_workspace_bytes(int64_t n, int dim);
+/* flags: bit0 = apply PixelNorm first (always set for Generator.style); bit1 = force the SIMT fp32
+ * kernels (reference-grade fp32 FMA path used to validate the tensor-core path).
+ * n_layers == 0 with bit0 set runs PixelNorm alone (d_packed may be NULL). */
+int gsb_mapping_forward(const void *d_packed, int n_layers, int dim, const float *d_z, float *d_w,
+                        int64_t n, int flags, void *d_workspace, size_t workspace_bytes,
+                        gsb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-batch sufficient statistics of the incremental PCA (Gram form):
+ *   mean[d] (fp64) and centred Gram (X-mean)^T (X-mean) [d,d] (fp64, full symmetric) of X[n,d] fp32
+ *   (row stride ld floats).  Together with n they carry everything IncrementalPCA.partial_fit
+ *   (estimators.py:68-76 -> sklearn _incremental_pca.py:254-380) extracts from the batch.
+ * ---------------------------------------------------------------------------------------------- */
+size_t gsb_batch_stats_workspace_bytes(int64_t n, int d);
+int gsb_batch_stats(const float *d_x, int64_t n, int d, int64_t ld, double *d_mean, double *d_gram,
+                    void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Incremental-PCA chain (small-d engine, d <= 1024, d % 32 == 0).
+ *   replaces  estimators.py:55-81 IPCAEstimator.fit_partial/get_components, i.e. sklearn
+ *   IncrementalPCA.partial_fit: running mean/var merge (extmath.py:1118-1265), rank-c truncated
+ *   merge  G = V^T S^2 V + Xc^T Xc + m m^T  -> symmetric eigensolve (Householder tridiagonalisation,
+ *   bisection, inverse iteration, back-transform; all fp64, on device) -> top-c -> svd_flip sign rule.
+ *   The state lives in device memory; chain steps must be enqueued in the reference's batch order.
+ * ---------------------------------------------------------------------------------------------- */
+size_t gsb_ipca_state_bytes(int d, int c);
+size_t gsb_ipca_workspace_bytes(int d, int c);
+int gsb_ipca_reset(void *d_state, int d, int c, gsb_stream_t stream);
+/* n_seen = samples merged before this step (the host tracks it; 0 for the first step). */
+int gsb_ipca_chain_step(void *d_state, int d, int c, int64_t n_seen, int64_t n_batch,
+                        const double *d_mean_b, const double *d_gram_b,
+                        void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
+/* Export sklearn's attributes (any pointer may be NULL): components_[c,d], singular_values_[c],
+ * mean_[d], var_[d], explained_variance_[c], explained_variance_ratio_[c] -- all fp64. */
+int gsb_ipca_export(const void *d_state, int d, int c, int64_t n_seen,
+                    double *d_components, double *d_singular_values, double *d_mean, double *d_var,
+                    double *d_explained_variance, double *d_explained_variance_ratio,
+                    gsb_stream_t stream);
+
+/* Stand-alone symmetric eigensolver used by the chain (test hook): top-c eigenpairs of the fp64
+ * symmetric matrix d_a[d,d] (destroyed); d_evals[c] descending, d_evecs[c,d] rows, sign-normalised. */
+int gsb_sym_eig_top(double *d_a, int d, int c, double *d_evals, double *d_evecs,
+                    void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Projection statistics:  out_std[k] = population std over rows r<n of  dirs[k,:] . (x[r,:] - sub[:])
+ *   replaces  decomposition.py:313-316 (random_stdevs) and :326-329 (lat_stdev).  d_sub may be NULL.
+ *   Projections in fp32 FMA, moments in fp64.
+ * ---------------------------------------------------------------------------------------------- */
+size_t gsb_project_std_workspace_bytes(int c);
+int gsb_project_std(const float *d_x, int64_t n, int d, int64_t ld, const float *d_dirs, int c,
+                    const double *d_sub, float *d_out_std, void *d_workspace, size_t workspace_bytes,
+                    gsb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Latent regression accumulators (Z-space runs):
+ *   replaces  decomposition.py:77-139 linreg_lstsq: per batch  act = x - mean; A = (act . comp^T)/stdev;
+ *   accumulates the normal equations  AtA[c,c] += A^T A,  AtZ[c,L] += A^T Z,  sumZ[L] += sum Z  (fp64)
+ *   so the 1e6 x (c + L) host matrices of the reference never exist; gsb_linreg_solve returns
+ *   M_t = (AtA)^-1 AtZ (Cholesky, fp64), the least-squares solution scipy.linalg.lstsq(gelsd) gives
+ *   for the full-column-rank A.
+ * ---------------------------------------------------------------------------------------------- */
+size_t gsb_linreg_state_bytes(int c, int latent_dim);
+int gsb_linreg_reset(void *d_state, int c, int latent_dim, gsb_stream_t stream);
+int gsb_linreg_accumulate(void *d_state, int c, int latent_dim, const float *d_act, int64_t n, int d,
+                          const float *d_comp, const float *d_mean, const float *d_stdev,
+                          const float *d_z, void *d_workspace, size_t workspace_bytes,
+                          gsb_stream_t stream);
+size_t gsb_linreg_workspace_bytes(int64_t n, int c);
+int gsb_linreg_solve(void *d_state, int c, int latent_dim, int64_t n_total, double *d_M_t,
+                     double *d_z_mean, gsb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GANSPACE_B200_H */

@@ -1,0 +1,164 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol; host logic mirrors the
+reference (Config, plan arithmetic, cache naming, estimator surface, hooks); the product never touches
+the oracle."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    from ganspace_b200 import _native
+    header = (ROOT / "include" / "ganspace_b200.h").read_text()
+    declared = set(re.findall(r"\b(gsb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    lib = ctypes.CDLL(str(_native.lib_path()))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _native.load().gsb_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    from ganspace_b200 import _native
+    with pytest.raises(_native.NativeError):
+        _native.require_cuda("cuda")
+    with pytest.raises(_native.NativeError):
+        _native.require_cuda("cpu")
+    from ganspace_b200.models import StyleGAN2
+    with pytest.raises(_native.NativeError):
+        StyleGAN2(torch.device("cpu"), "ffhq", random_init=1234)
+    lib = _native.load()
+    rc = lib.gsb_ipca_reset(ctypes.c_void_p(256), 512, 80, ctypes.c_void_p(0))
+    assert rc == -2 and b"cuda" in lib.gsb_last_error().lower()
+
+
+def test_product_never_imports_oracle():
+    for p in (ROOT / "ganspace_b200").rglob("*.py"):
+        txt = p.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), p
+        assert "ganspace_oracle" not in txt, p
+    for p in (ROOT / "ganspace_b200" / "csrc").glob("*.cu*"):
+        assert "oracle/" not in p.read_text(), p
+
+
+def test_config_defaults_and_flags():
+    from ganspace_b200.config import Config
+    c = Config()
+    assert (c.model, c.layer, c.estimator, c.components, c.n, c.use_w) == ("StyleGAN", "g_mapping", "ipca", 80, 300_000, False)
+    assert c.batch_size is None and c.seed is None and c.sparsity == 1.0 and c.sigma == 2.0
+    c = Config(model="StyleGAN2", n=10, use_w=True, extra=3)
+    assert c.model == "StyleGAN2" and c.n == 10 and c.use_w and c.extra == 3
+    c = Config().from_args(["--model", "BigGAN-512", "--class", "husky", "-b", "7", "-c", "3", "-n", "9", "--use_w",
+                            "--est", "ipca", "--seed", "4", "--layer", "generator.gen_z"])
+    assert (c.model, c.output_class, c.batch_size, c.components, c.n, c.use_w, c.seed) == \
+        ("BigGAN-512", "husky", 7, 3, 9, True, 4)
+    assert '"custom"' in str(c)
+
+
+@pytest.mark.parametrize("n,B,c,expect", [
+    (10_000, 1_000, 32, (10_000, 2_000, 12_000, 5)),
+    (1_000_000, 10_000, 80, (1_000_000, 10_000, 1_010_000, 100)),
+    (5_000, 700, 20, (4_900, 2_000, 7_000, 3)),
+    (300_000, 20, 80, (300_000, 2_000, 302_000, 150)),
+    (9_000, 1_000, 800, (9_000, 2_400, 12_000, 4)),
+])
+def test_plan_matches_reference_arithmetic(oracle, n, B, c, expect):
+    from ganspace_b200 import plan
+    p = plan.make_plan(n, B, c)
+    assert (p.N, p.NB, p.n_lat, p.K) == expect
+    assert (p.N, p.NB, p.n_lat, p.K) == oracle.plan(n, B, c)
+    # every group's rows are covered by the generated batches
+    for k in range(p.K):
+        r0, r1 = p.group_rows(k)
+        b0, b1 = p.batches_covering(r0, r1)
+        assert b0 * B <= r0 and b1 * B >= r1 and b1 <= p.n_calls
+
+
+def test_sharding_partitions_groups():
+    from ganspace_b200 import plan
+    p = plan.make_plan(1_000_000, 10_000, 80)
+    for world in (1, 2, 4, 8):
+        owned = [[k for k in plan.groups_to_process(p, r, world) if plan.owner(k, world) == r] for r in range(world)]
+        assert sorted(sum(owned, [])) == list(range(p.K))
+        for r in range(world):
+            assert p.K - 1 in plan.groups_to_process(p, r, world)
+    assert plan.contiguous_runs([0, 1, 2, 5, 6, 9]) == [[0, 1, 2], [5, 6], [9]]
+
+
+def test_estimator_surface_and_cache_name():
+    from ganspace_b200.estimators import get_estimator
+    est = get_estimator("ipca", 80, 1.0)
+    assert est.batch_support and est.get_param_str() == "ipca_c80"
+    assert est.transformer.batch_size == 160 and int(est.transformer.n_samples_seen_) == 0
+    with pytest.raises(RuntimeError, match="Unknown estimator"):
+        get_estimator("nope", 3, 1.0)
+    with pytest.raises(RuntimeError):
+        get_estimator("pca", 3, 1.0)
+
+
+def test_get_random_dirs_matches_reference_formula():
+    from ganspace_b200.decomposition import get_random_dirs, SEED_RANDOM_DIRS
+    d = get_random_dirs(5, 64)
+    g = np.random.RandomState(SEED_RANDOM_DIRS).normal(size=(5, 64))
+    g /= np.sqrt(np.sum(g ** 2, axis=1, keepdims=True))
+    assert d.dtype == np.float32 and np.array_equal(d, g.astype(np.float32))
+
+
+class _Toy(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(4, 4)
+        self.b = torch.nn.Sequential(torch.nn.ReLU(), torch.nn.Linear(4, 2))
+
+    def forward(self, x):
+        return self.b(self.a(x))
+
+
+def test_instrumented_model_retain_edit_close():
+    from ganspace_b200.netdissect.nethook import InstrumentedModel
+    torch.manual_seed(0)
+    toy = _Toy()
+    x = torch.randn(3, 4)
+    base = toy(x)
+    ax = torch.nn.functional.linear(x, toy.a.weight, toy.a.bias)      # un-hooked value of layer 'a'
+    tail = lambda h: torch.nn.functional.linear(torch.relu(h), toy.b[1].weight, toy.b[1].bias)
+    inst = InstrumentedModel(toy)
+    inst.retain_layer("a")
+    assert inst.retained_features()["a"] is None
+    out = inst(x)
+    assert torch.equal(out, base) and torch.equal(inst.retained_layer("a"), ax)
+    inst.edit_layer("a", offset=torch.ones(4))
+    assert torch.allclose(inst(x), tail(ax + 1))
+    assert torch.equal(inst.retained_layer(), ax)                     # retained before the edit
+    inst.edit_layer("a", ablation=1.0, replacement=torch.zeros(4))
+    assert torch.allclose(inst(x), tail(torch.ones(3, 4)))            # x*(1-1) + 0*1, then +offset
+    inst.remove_edits("a", remove_offset=False)
+    assert torch.allclose(inst(x), tail(ax + 1))
+    inst.remove_edits()
+    assert torch.equal(inst(x), base)
+    with pytest.raises(ValueError, match="not found"):
+        inst.retain_layer("nope")
+    inst.close()
+    assert torch.equal(toy(x), base) and not inst.retained_features()
+
+
+def test_generator_module_tree_and_init_order(golden):
+    from ganspace_b200.models import stylegan2
+    torch.manual_seed(1234)
+    g = stylegan2.Generator(1024, 512, 8)
+    names = [n for n, _ in g.named_modules()]
+    assert len(names) == 163 and g.n_latent == 18
+    for must in ("style", "style.8", "input", "conv1", "to_rgb1", "convs.0", "convs.15", "to_rgbs.7", "convs.4.conv.modulation"):
+        assert must in names, must
+    gold = golden("mapping_known_answers.npz")
+    sd = g.state_dict()
+    assert np.allclose([float(sd[f"style.{i + 1}.weight"].double().sum()) for i in range(8)], gold["style_weight_sums"])
+    if "synth_param_sums" in gold:
+        keys = [str(k) for k in gold["synth_param_keys"]]
+        assert np.allclose([float(sd[k].double().sum()) for k in keys], gold["synth_param_sums"])

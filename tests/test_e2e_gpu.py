@@ -1,0 +1,83 @@
+"""End-to-end parity of get_or_compute() (public API -> C ABI -> CUDA) against the committed golden
+fixtures produced by the unmodified reference, and against the oracle at other sizes."""
+import tempfile
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+COS_TOL = 0.999        # BASELINE.json: sign-normalised cosine >= 0.999 for the top-c components
+RATIO_TOL = 1e-3       # BASELINE.json: explained-variance ratios within 1e-3
+
+
+def _run(n, b, c, use_w, outclass="ffhq", seed=None):
+    from ganspace_b200.config import Config
+    from ganspace_b200.decomposition import get_or_compute
+    from ganspace_b200.models import get_instrumented_model, StyleGAN2
+    dev = torch.device("cuda:0")
+    model = StyleGAN2(dev, outclass, random_init=1234)
+    inst = get_instrumented_model("StyleGAN2", outclass, "style", dev, model=model, use_w=use_w)
+    cfg = Config(model="StyleGAN2", layer="style", output_class=outclass, components=c, n=n, batch_size=b,
+                 use_w=use_w, estimator="ipca", seed=seed)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = get_or_compute(cfg, inst, submit_config=SimpleNamespace(run_dir=tmp, run_dir_root=tmp),
+                              force_recompute=True)
+        with np.load(path, allow_pickle=False) as data:
+            out = {k: data[k] for k in data.files}
+    inst.close()
+    return out, path.name
+
+
+def _check(cmp, lat_tol=COS_TOL):
+    assert cmp["min_signed_cos"] >= COS_TOL, cmp
+    assert cmp["max_abs_dvar_ratio"] <= RATIO_TOL, cmp
+    assert cmp["min_lat_signed_cos"] >= lat_tol, cmp
+    assert cmp["act_mean_rel"] < 1e-5 and cmp["act_stdev_rel"] < 1e-4, cmp
+    assert cmp["lat_stdev_rel"] < 1e-3 and cmp["random_stdevs_rel"] < 1e-3, cmp
+
+
+def test_config1_vs_reference_golden(golden, oracle):
+    g = golden("c1_stylegan2_ffhq_style_w_n10000_b1000_c32.npz")
+    out, name = _run(10_000, 1_000, 32, True)
+    assert name == str(g["dump_name"])
+    for k in ("act_comp", "act_mean", "act_stdev", "lat_comp", "lat_mean", "lat_stdev", "var_ratio", "random_stdevs"):
+        assert out[k].shape == g[k].shape and out[k].dtype == np.float32, k
+    _check(oracle.compare_npz(out, g))
+
+
+def test_ragged_plan_and_seed_vs_reference_golden(golden, oracle):
+    g = golden("w_ragged_n5000_b700_c20_seed7.npz")
+    out, name = _run(5_000, 700, 20, True, seed=7)
+    assert name == str(g["dump_name"])
+    _check(oracle.compare_npz(out, g))
+
+
+def test_z_space_regression_vs_reference_golden(golden, oracle):
+    g = golden("c3s_stylegan2_car_style_z_n4000_b1000_c16.npz")
+    out, name = _run(4_000, 1_000, 16, False, outclass="car")
+    assert name == str(g["dump_name"])
+    cmp = oracle.compare_npz(out, g)
+    _check(cmp)
+    assert cmp["lat_mean_rel"] < 1e-4, cmp
+    assert np.array_equal(out["lat_stdev"], np.ones(16, np.float32))
+
+
+def test_w_space_c80_vs_oracle(oracle, mapping_weights):
+    ws, bs = mapping_weights
+    ref = oracle.compute_stylegan2_style(ws, bs, 40_000, 10_000, 80, True)
+    out, _ = _run(40_000, 10_000, 80, True)
+    _check(oracle.compare_npz(out, ref))
+
+
+def test_cache_hit_and_validation_errors():
+    from ganspace_b200.config import Config
+    from ganspace_b200.decomposition import get_or_compute
+    with pytest.raises(RuntimeError, match="Must specify number of samples"):
+        get_or_compute(Config(model="StyleGAN2", output_class="ffhq", layer="style", n=None))
+    with pytest.raises(RuntimeError, match="InstrumentedModel"):
+        get_or_compute(Config(model="StyleGAN2", output_class="ffhq", layer="style", n=100), model=object())
+    with pytest.raises(RuntimeError, match="Cannot change latent space"):
+        get_or_compute(Config(model="BigGAN-512", output_class="husky", layer="generator.gen_z", n=100, use_w=True))

@@ -1,0 +1,54 @@
+"""Pins the oracle (numpy restatement) to the golden fixtures written by the unmodified reference
+(oracle/gen_golden.py).  Tolerances: fp32 summation-order noise only."""
+import numpy as np
+import pytest
+
+
+def test_mapping_init_and_forward(oracle, golden, mapping_weights):
+    g = golden("mapping_known_answers.npz")
+    ws, bs = mapping_weights
+    assert np.allclose([float(w.astype(np.float64).sum()) for w in ws], g["style_weight_sums"])
+    assert np.array_equal(ws[0][:4, :8], g["style1_weight_head"])
+    out = oracle.mapping_forward(g["z"], ws, bs)
+    assert np.max(np.abs(out - g["w"])) < 2e-5
+
+
+@pytest.mark.parametrize("form", ["svd", "gram"])
+def test_ipca_chain_restatement_vs_sklearn(oracle, golden, form):
+    g = golden("ipca_chain_d96_c12.npz")
+    st = oracle.IPCAState(12)
+    for k, X in enumerate(g["X"]):
+        if form == "svd":
+            oracle.ipca_partial_fit(st, X)
+        else:
+            oracle.ipca_gram_step(st, *oracle.batch_stats(X))
+        cos = np.sum(st.components * g[f"comp_{k}"], axis=1)
+        assert np.min(cos) > 1 - 1e-6
+        assert np.allclose(st.singular_values, g[f"sv_{k}"], rtol=1e-5)
+        assert np.allclose(np.sqrt(st.explained_variance), g[f"stdev_{k}"], rtol=1e-5)
+        assert np.allclose(st.explained_variance_ratio, g[f"ratio_{k}"], atol=1e-7)
+        assert np.allclose(st.mean, g[f"mean_{k}"], rtol=1e-10, atol=1e-10)
+        assert np.allclose(st.var, g[f"var_{k}"], rtol=1e-6)
+
+
+CASES = [
+    ("c1_stylegan2_ffhq_style_w_n10000_b1000_c32.npz", dict(n=10_000, B=1_000, c=32, use_w=True)),
+    ("w_ragged_n5000_b700_c20_seed7.npz", dict(n=5_000, B=700, c=20, use_w=True, seed=7)),
+    ("c3s_stylegan2_car_style_z_n4000_b1000_c16.npz", dict(n=4_000, B=1_000, c=16, use_w=False)),
+]
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+@pytest.mark.parametrize("form", ["svd", "gram"])
+def test_compute_restatement_vs_reference(oracle, golden, mapping_weights, name, kw, form):
+    g = golden(name)
+    ws, bs = mapping_weights
+    out = oracle.compute_stylegan2_style(ws, bs, kw["n"], kw["B"], kw["c"], kw["use_w"], seed=kw.get("seed"),
+                                         ipca=form)
+    cmp = oracle.compare_npz(out, g)
+    assert cmp["min_signed_cos"] > 1 - 1e-6 and cmp["min_lat_signed_cos"] > 1 - 1e-6, cmp
+    assert cmp["max_abs_dvar_ratio"] < 1e-6, cmp
+    for k in ("act_mean_rel", "act_stdev_rel", "lat_mean_rel", "lat_stdev_rel", "random_stdevs_rel"):
+        assert cmp[k] < 1e-5, (k, cmp)
+    for k in out:
+        assert out[k].shape == g[k].shape and out[k].dtype == g[k].dtype, k
