@@ -1,0 +1,264 @@
+"""bench.py -- latent samples/sec into PCA (BASELINE.json metric) on N B200s.
+
+Workload (BASELINE.json configs[1]): StyleGAN2-ffhq (random-init weights, torch.manual_seed(1234)),
+layer=style --use_w, N=1_000_000 b=10_000 c=80, estimator=ipca.  One "step" = one whole
+get_or_compute(force_recompute=True) over the N samples (synthetic data: the latents ARE the data).
+
+  value   N / device time of decomposition.compute_arrays() (CUDA events; seeds/weights resident; no file)
+  e2e     N / wall time of the public get_or_compute() call: host seeds -> H2D, components D2H, .npz written
+  roofline  the mapping-MLP kernels (north_star's roofline): 4,194,304 FLOP per latent (8 x 2*512*512),
+            timed live with CUDA events around every mapping launch inside the timed steps, against the
+            measured bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline  the oracle's restatement of the reference path on the host cores, bounded sample
+
+--impl reference times the reference's CPU implementation of the path (the oracle port: the reference is
+pure Python and cannot travel to the GPU box) with all host threads, one bounded sample
+per step.  Multi-GPU: launched by torchrun, one rank per GPU, NCCL; weak/strong: the job's N is fixed
+(strong scaling of the one PCA job).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+from types import SimpleNamespace
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FLOP_PER_SAMPLE = 8 * 2 * 512 * 512
+METRIC = "latent samples/sec into PCA (StyleGAN2-ffhq W, N=1e6)"
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.lines, self.gpu = None, [], gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower() == "active":
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _cpu_baseline(n_sample, B, c, threads=None):
+    """The oracle port of the reference path on the host cores (bounded sample)."""
+    from oracle import ganspace_oracle as orc
+    ws, bs = orc.mapping_random_init(1234)
+    t0 = time.perf_counter()
+    orc.compute_stylegan2_style(ws, bs, n_sample, B, c, True, ipca="svd")
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np  # noqa
+    n_sample = args.ref_sample
+    cores = os.cpu_count()
+    times = []
+    for i in range(args.warmup + args.steps):
+        v, dt = _cpu_baseline(n_sample, args.batch, args.components)
+        if i >= args.warmup:
+            times.append(dt)
+    dt = sum(times) / len(times)
+    value = n_sample / dt
+    sample = f"N={n_sample} of the same config per step (b={args.batch}, c={args.components}); oracle port, numpy/scipy BLAS threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"StyleGAN2-ffhq random-init W-space PCA (layer=style --use_w), b={args.batch} c={args.components}, "
+                               f"CPU sample N={n_sample}"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ganspace_b200 import _native
+    from ganspace_b200.config import Config
+    from ganspace_b200 import decomposition
+    from ganspace_b200.models import get_instrumented_model, StyleGAN2
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _native.load()
+
+    model = StyleGAN2(dev, "ffhq", random_init=1234)
+    inst = get_instrumented_model("StyleGAN2", "ffhq", "style", dev, model=model, use_w=True)
+
+    def cfg():
+        return Config(model="StyleGAN2", layer="style", output_class="ffhq", components=args.components, n=args.n,
+                      batch_size=args.batch, use_w=True, estimator="ipca")
+
+    tmp = tempfile.mkdtemp(prefix="gsb_bench_")
+    sub = SimpleNamespace(run_dir=tmp, run_dir_root=tmp)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    devnull = open(os.devnull, "w")
+
+    def quiet(fn):
+        old = sys.stdout
+        sys.stdout = devnull
+        try:
+            return fn()
+        finally:
+            sys.stdout = old
+
+    # ---- warm-up (both entry points) ----------------------------------------------------------------
+    for _ in range(args.warmup):
+        quiet(lambda: decomposition.compute_arrays(cfg(), inst))
+    quiet(lambda: decomposition.get_or_compute(cfg(), inst, submit_config=sub, force_recompute=True))
+
+    # ---- timed: device pipeline (value) + live per-kernel sections (roofline) -------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _native.instrument.reset()
+    _native.instrument.timing = True
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        quiet(lambda: decomposition.compute_arrays(cfg(), inst))
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1) / args.steps
+    sections = _native.instrument.section_ms()
+    launches = _native.instrument.launches
+    _native.instrument.timing = False
+
+    # ---- timed: end to end through the public API (host seeds in, .npz out) ---------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        path = quiet(lambda: decomposition.get_or_compute(cfg(), inst, submit_config=sub, force_recompute=True))
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pl = decomposition._plan.make_plan(args.n, args.batch, args.components)
+        N = pl.N
+        peaks, peak_kind = _peaks()
+        map_ms, map_calls = sections.get("mapping", (0.0, 0))
+        rows_mapped = (pl.n_lat // world if world > 1 else pl.n_lat) + 5000 + 2   # per step, this rank (approx. when sharded)
+        map_ms_step = map_ms / args.steps
+        achieved = rows_mapped * FLOP_PER_SAMPLE / (map_ms_step * 1e-3) / 1e12 if map_ms_step > 0 else None
+        peak = peaks["bf16_tflops_sustained"]
+        with np.load(path) as data:
+            d2h = int(sum(data[k].nbytes for k in data.files))
+        out = {
+            "metric": METRIC, "value": N / (dev_ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"StyleGAN2-ffhq random-init W-space PCA (layer=style --use_w), N={args.n} b={args.batch} "
+                                   f"c={args.components}, estimator=ipca (BASELINE.json configs[1])",
+                       "parallelism": f"groups k mod {world}, one all-reduce of per-group stats" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (2.07 GB of latents per step), no flush needed"},
+            "e2e": {"value": N / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 4 * (pl.n_calls + 1), "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "mapping MLP (pixelnorm + 8 x sgemm_tn_bias_act_kernel)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "peak_source": f"bf16_tflops_sustained, {peak_kind} (MEASURED_PEAKS.json)",
+                         "ms_per_step": map_ms_step, "launches_per_step": map_calls / max(1, args.steps)},
+            "sections_ms_per_step": {k: v[0] / args.steps for k, v in sections.items()},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt = _cpu_baseline(args.ref_sample, args.batch, args.components)
+            out["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"N={args.ref_sample} of the same config (b={args.batch}, c={args.components}), "
+                                             f"{dt:.1f} s of CPU work; oracle port with numpy/scipy BLAS threads"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--batch", type=int, default=10_000)
+    ap.add_argument("--components", type=int, default=80)
+    ap.add_argument("--ref-sample", dest="ref_sample", type=int, default=100_000)
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -26,6 +26,7 @@ SIGNATURES = {
     "gsb_mapping_pack": (_I, [_P, _P, _I, _I, _F, _P, _P]),
     "gsb_mapping_workspace_bytes": (_Z, [_L, _I]),
     "gsb_mapping_forward": (_I, [_P, _I, _I, _P, _P, _L, _I, _P, _Z, _P]),
+    "gsb_mapping_status": (_I, [_P, _I, _I, _P]),
     "gsb_batch_stats_workspace_bytes": (_Z, [_L, _I]),
     "gsb_batch_stats": (_I, [_P, _L, _I, _L, _P, _P, _P, _Z, _P]),
     "gsb_ipca_state_bytes": (_Z, [_I, _I]),
@@ -209,6 +210,10 @@ def mt19937_raw(seeds, n_per_stream: int, device) -> torch.Tensor:
     return out
 
 
+# default mapping-network path: "tc" = tcgen05 fp16x3 split (fp32-grade), "simt" = fp32 FMA kernels
+MAPPING_DEFAULT = "tc"
+
+
 class PackedMapping:
     """Pre-scaled mapping-network weights in the layout the kernels read (gsb_mapping_pack)."""
 
@@ -225,9 +230,21 @@ class PackedMapping:
             _check(lib.gsb_mapping_pack(_ptr(w), _ptr(b), self.n_layers, self.dim, float(lr_mul),
                                         _ptr(self.packed), _stream()), "gsb_mapping_pack")
 
+    def check(self):
+        """Raise if the tensor-core path saw an activation outside fp16's range (synchronises)."""
+        flags = C.c_uint(0)
+        with torch.cuda.device(self.device):
+            _check(load().gsb_mapping_status(_ptr(self.packed), self.n_layers, self.dim, C.byref(flags)),
+                   "gsb_mapping_status")
+        if flags.value & 1:
+            raise NativeError("mapping network: an activation exceeded fp16 range in the tensor-core path; "
+                              "results are invalid (set GANSPACE_B200_MAPPING=simt)")
+
     def forward(self, z: torch.Tensor, out: torch.Tensor = None, pixelnorm: bool = True,
-                force_simt: bool = False) -> torch.Tensor:
+                force_simt: bool = None) -> torch.Tensor:
         lib = load()
+        if force_simt is None:
+            force_simt = os.environ.get("GANSPACE_B200_MAPPING", MAPPING_DEFAULT) == "simt"
         assert z.is_cuda and z.dtype == torch.float32 and z.shape[-1] == self.dim
         z2 = z.reshape(-1, self.dim)
         if not z2.is_contiguous():

@@ -14,6 +14,19 @@
 
 namespace gsb {
 
+// tensor-core path (mapping_tc.cu)
+size_t mapping_tc_packed_bytes(int n_layers, int dim);
+int mapping_tc_pack(const float *pw, int n_layers, int dim, void *tc_base, cudaStream_t st);
+int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim, const float *d_z, float *d_w,
+                       int64_t n, bool pixelnorm, void *ws, cudaStream_t st);
+size_t mapping_tc_workspace_bytes(int64_t n, int dim);
+unsigned *mapping_tc_overflow_flag(void *tc_base, int n_layers, int dim);
+
+static inline size_t simt_packed_bytes(int n_layers, int dim) {
+    return align_up(((size_t)n_layers * dim * dim + (size_t)n_layers * dim) * sizeof(float), 256);
+}
+static inline bool tc_supported(int n_layers, int dim) { return n_layers > 0 && dim % 256 == 0; }
+
 __global__ void mapping_pack_kernel(const float *__restrict__ w, const float *__restrict__ b,
                                     int n_layers, int dim, float scale, float lr_mul,
                                     float *__restrict__ pw, float *__restrict__ pb) {
@@ -167,7 +180,7 @@ int mapping_forward_simt(const float *pw, const float *pb, int n_layers, int dim
 }  // namespace gsb
 
 extern "C" size_t gsb_mapping_packed_bytes(int n_layers, int dim) {
-    return ((size_t)n_layers * dim * dim + (size_t)n_layers * dim) * sizeof(float);
+    return gsb::simt_packed_bytes(n_layers, dim) + (gsb::tc_supported(n_layers, dim) ? gsb::mapping_tc_packed_bytes(n_layers, dim) : 0);
 }
 
 extern "C" int gsb_mapping_pack(const float *d_weight, const float *d_bias, int n_layers, int dim,
@@ -182,11 +195,17 @@ extern "C" int gsb_mapping_pack(const float *d_weight, const float *d_bias, int 
     gsb::mapping_pack_kernel<<<512, 256, 0, (cudaStream_t)stream>>>(d_weight, d_bias, n_layers, dim, scale,
                                                                    lr_mul, pw, pb);
     GSB_CHECK_LAUNCH();
+    if (gsb::tc_supported(n_layers, dim)) {
+        void *tc_base = reinterpret_cast<char *>(d_packed) + gsb::simt_packed_bytes(n_layers, dim);
+        return gsb::mapping_tc_pack(pw, n_layers, dim, tc_base, (cudaStream_t)stream);
+    }
     return GSB_OK;
 }
 
 extern "C" size_t gsb_mapping_workspace_bytes(int64_t n, int dim) {
-    return 2 * gsb::align_up((size_t)n * dim * sizeof(float), 256);
+    size_t simt = 2 * gsb::align_up((size_t)n * dim * sizeof(float), 256);
+    size_t tc = gsb::mapping_tc_workspace_bytes(n, dim);
+    return simt > tc ? simt : tc;
 }
 
 extern "C" int gsb_mapping_forward(const void *d_packed, int n_layers, int dim, const float *d_z,
@@ -203,9 +222,24 @@ extern "C" int gsb_mapping_forward(const void *d_packed, int n_layers, int dim, 
     }
     const float *pw = reinterpret_cast<const float *>(d_packed);
     const float *pb = pw + (size_t)n_layers * dim * dim;
+    if (!(flags & 2) && gsb::tc_supported(n_layers, dim)) {
+        void *tc_base = reinterpret_cast<char *>(const_cast<void *>(d_packed)) + gsb::simt_packed_bytes(n_layers, dim);
+        return gsb::mapping_forward_tc(pb, tc_base, n_layers, dim, d_z, d_w, n, (flags & 1) != 0, d_workspace,
+                                       (cudaStream_t)stream);
+    }
     float *tmp0 = reinterpret_cast<float *>(d_workspace);
     float *tmp1 = reinterpret_cast<float *>(reinterpret_cast<char *>(d_workspace) +
                                             gsb::align_up((size_t)n * dim * sizeof(float), 256));
     return gsb::mapping_forward_simt(pw, pb, n_layers, dim, d_z, d_w, n, (flags & 1) != 0, tmp0, tmp1,
                                      (cudaStream_t)stream);
+}
+
+extern "C" int gsb_mapping_status(const void *d_packed, int n_layers, int dim, unsigned *h_flags) {
+    GSB_CHECK_ARG(d_packed && h_flags, "mapping_status: null pointer");
+    *h_flags = 0;
+    if (!gsb::tc_supported(n_layers, dim)) return GSB_OK;
+    void *tc_base = reinterpret_cast<char *>(const_cast<void *>(d_packed)) + gsb::simt_packed_bytes(n_layers, dim);
+    GSB_CHECK_CUDA(cudaMemcpy(h_flags, gsb::mapping_tc_overflow_flag(tc_base, n_layers, dim), sizeof(unsigned),
+                              cudaMemcpyDeviceToHost));
+    return GSB_OK;
 }

@@ -1,0 +1,482 @@
+// StyleGAN2 mapping network on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), fp32-grade accuracy.
+//
+// Replaces models/stylegan2/stylegan2-pytorch/model.py:151-161 (EqualLinear.forward: F.linear(x, W*scale)
+// then fused bias + leaky-ReLU(0.2)*sqrt2, op/fused_act.py:86-92) for the 8 layers of Generator.style.
+//
+// Precision.  The parity target (principal directions vs sklearn on the same seeds, cos >= 0.999 at relative
+// eigen-gaps of 0.27 %) needs ~1e-6 relative accuracy per layer: single-pass bf16/fp16 (2^-9 / 2^-12) fails
+// it (SURVEY.md section 7 hard part 3).  Each fp32 operand is split into two fp16 numbers, x = hi + lo with
+// hi = fp16(x), lo = fp16(x - hi)  (22 significant bits), and the product is formed from three MMAs
+//     D += A_hi W_hi ;  D += A_lo W_hi ;  D += A_hi W_lo          (fp32 accumulation in TMEM)
+// dropping only the lo*lo term (2^-24).  Weights are pre-scaled by a per-layer power of two so that W_lo
+// stays in fp16's normal range; the scale is undone exactly in the epilogue.  fp16 (11-bit significand) at
+// the bf16 MMA rate gives this accuracy in 3 MMAs; TF32 would need 3 MMAs at half the rate.
+//
+// Kernel (one launch per layer; activations travel between layers as fp16 hi/lo pairs = the same 4 B/element
+// as fp32): persistent, one CTA per SM, warp-specialised:
+//     warp 0   TMA producer   (A_hi, A_lo: 128 x 64 boxes; W_hi, W_lo: 256 x 64 boxes; SWIZZLE_128B, K-major)
+//     warp 1   MMA issuer     (one thread: tcgen05.mma.cta_group::1.kind::f16, M128 N256 K16, 12 per K-block)
+//     warp 2   TMEM allocator (512 columns = two 128x256 fp32 accumulators, so the epilogue of tile i
+//                              overlaps the MMAs of tile i+1)
+//     warps 4-7 epilogue      (tcgen05.ld 32x32b -> 2^-s, +bias, leaky-ReLU, *sqrt2 -> split to fp16 hi/lo
+//                              for the next layer, or fp32 for the last layer)
+// smem ring: 2 stages x 96 KB (A_hi 16K, A_lo 16K, W_hi 32K, W_lo 32K), mbarrier full/empty pairs.
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+namespace gsb {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_N = 256;
+constexpr int TC_BLOCK_K = 64;           // 64 fp16 = one 128-byte swizzle row
+constexpr int TC_UMMA_K = 16;
+constexpr int TC_STAGES = 2;
+constexpr int TC_ACC_STAGES = 2;
+constexpr int TC_THREADS = 256;
+constexpr uint32_t TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
+constexpr uint32_t TC_W_BYTES = TC_BLOCK_N * TC_BLOCK_K * 2;   // 32 KB
+constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_W_BYTES;   // 96 KB
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
+//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b_format F16 (0) @7/@10,
+// a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcParams {
+    const float *bias;      // [N_total] pre-multiplied by lr_mul
+    __half *out_hi;         // next layer's A_hi [M, N_total] (nullptr on the last layer)
+    __half *out_lo;
+    float *out_f32;         // fp32 output [M, N_total] (last layer)
+    unsigned *overflow;     // set to 1 when an activation leaves fp16's range
+    const float *inv_wscale;   // device pointer to 2^-s of this layer
+    int M, N_total, K;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                        const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                        const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t *full_bar = bars;                         // [TC_STAGES]
+    uint64_t *empty_bar = bars + TC_STAGES;            // [TC_STAGES]
+    uint64_t *tfull_bar = bars + 2 * TC_STAGES;        // [TC_ACC_STAGES]
+    uint64_t *tempty_bar = tfull_bar + TC_ACC_STAGES;  // [TC_ACC_STAGES]
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tempty_bar + TC_ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m_tiles = (p.M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+    const int num_n_tiles = p.N_total / TC_BLOCK_N;
+    const int num_tiles = num_m_tiles * num_n_tiles;
+    const int num_k_blocks = p.K / TC_BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
+        tma_prefetch_desc(&tm_w_hi); tma_prefetch_desc(&tm_w_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / num_n_tiles) * TC_BLOCK_M, n0 = (tile % num_n_tiles) * TC_BLOCK_N;
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *st = smem + stage * TC_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+                    tma_load_2d(&tm_a_hi, &full_bar[stage], st, kb * TC_BLOCK_K, m0);
+                    tma_load_2d(&tm_a_lo, &full_bar[stage], st + TC_A_BYTES, kb * TC_BLOCK_K, m0);
+                    tma_load_2d(&tm_w_hi, &full_bar[stage], st + 2 * TC_A_BYTES, kb * TC_BLOCK_K, n0);
+                    tma_load_2d(&tm_w_lo, &full_bar[stage], st + 2 * TC_A_BYTES + TC_W_BYTES, kb * TC_BLOCK_K, n0);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(TC_BLOCK_M, TC_BLOCK_N);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BLOCK_N);
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);           // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * TC_STAGE_BYTES);
+                    const uint64_t d_ah = make_sw128_kmajor_desc(st);
+                    const uint64_t d_al = make_sw128_kmajor_desc(st + TC_A_BYTES);
+                    const uint64_t d_wh = make_sw128_kmajor_desc(st + 2 * TC_A_BYTES);
+                    const uint64_t d_wl = make_sw128_kmajor_desc(st + 2 * TC_A_BYTES + TC_W_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * TC_UMMA_K * 2) >> 4);   // +32 B per K step
+                        tc_mma_f16(tmem_d, d_ah + koff, d_wh + koff, idesc, (kb | k) ? 1u : 0u);
+                        tc_mma_f16(tmem_d, d_al + koff, d_wh + koff, idesc, 1u);
+                        tc_mma_f16(tmem_d, d_ah + koff, d_wl + koff, idesc, 1u);
+                    }
+                    tc_commit(&empty_bar[stage]);                 // frees the smem slot when the MMAs retire
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull_bar[acc]);                       // accumulator complete -> epilogue
+                if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (TMEM -> registers -> global) =====================
+        const int ew = warp - 4;                                   // == warp % 4: TMEM lane quadrant
+        const int row_in_tile = ew * 32 + lane;
+        const float sqrt2 = 1.41421356237309515f;
+        const float inv_wscale = __ldg(p.inv_wscale);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / num_n_tiles) * TC_BLOCK_M, n0 = (tile % num_n_tiles) * TC_BLOCK_N;
+            const int64_t row = (int64_t)m0 + row_in_tile;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TC_BLOCK_N);
+            bool ovf = false;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TC_BLOCK_N; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(taddr + (uint32_t)c0, v);
+                tc_wait_ld();
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __fmul_rn(__uint_as_float(v[j]), inv_wscale) + __ldg(&p.bias[n0 + c0 + j]);
+                    x = (x >= 0.f) ? x : __fmul_rn(x, 0.2f);
+                    f[j] = __fmul_rn(sqrt2, x);
+                }
+                if (row < p.M) {
+                    if (p.out_f32) {
+                        float4 *dst = reinterpret_cast<float4 *>(p.out_f32 + row * p.N_total + n0 + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    }
+                    if (p.out_hi) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            __half h0 = __float2half_rn(f[2 * j]), h1 = __float2half_rn(f[2 * j + 1]);
+                            __half l0 = __float2half_rn(f[2 * j] - __half2float(h0));
+                            __half l1 = __float2half_rn(f[2 * j + 1] - __half2float(h1));
+                            ovf |= (fabsf(f[2 * j]) > 60000.f) | (fabsf(f[2 * j + 1]) > 60000.f);
+                            hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                            lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                        }
+                        uint4 *dh = reinterpret_cast<uint4 *>(p.out_hi + row * p.N_total + n0 + c0);
+                        uint4 *dl = reinterpret_cast<uint4 *>(p.out_lo + row * p.N_total + n0 + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            if (ovf) atomicOr(p.overflow, 1u);
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);                        // 128 arrivals release the accumulator
+            if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---- operand preparation ------------------------------------------------------------------------------
+// PixelNorm (model.py:14-19) + split into fp16 hi/lo.  One warp per row.
+__global__ void pixelnorm_split_kernel(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo,
+                                       int64_t n, int dim, int do_norm, unsigned *overflow) {
+    int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int lane = threadIdx.x & 31;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + row * dim);
+    float r = 1.f;
+    if (do_norm) {
+        float s = 0.f;
+        for (int i = lane; i < dim / 4; i += 32) {
+            float4 v = xr[i];
+            s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+        s = warp_sum(s);
+        r = 1.0f / sqrtf(s / (float)dim + 1e-8f);
+    }
+    bool ovf = false;
+    for (int i = lane; i < dim / 4; i += 32) {
+        float4 v = xr[i];
+        float f[4] = {v.x * r, v.y * r, v.z * r, v.w * r};
+        __half h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            h[q] = __float2half_rn(f[q]);
+            l[q] = __float2half_rn(f[q] - __half2float(h[q]));
+            ovf |= fabsf(f[q]) > 60000.f;
+        }
+        uint2 ph, pl;
+        ph.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+        ph.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+        pl.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+        pl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+        reinterpret_cast<uint2 *>(hi + row * dim)[i] = ph;
+        reinterpret_cast<uint2 *>(lo + row * dim)[i] = pl;
+    }
+    if (ovf) atomicOr(overflow, 1u);
+}
+
+// per-layer power-of-two weight scale: the largest |w'| = |w| 2^s lands in [8192, 16384), so that hi keeps
+// its 11 bits and lo (<= 2^-12 |w'|) stays a normal fp16 number.  scales[0] = 2^s, scales[1] = 2^-s.
+__global__ void pick_wscale_kernel(const float *__restrict__ absmax, float *__restrict__ wscale,
+                                   float *__restrict__ inv_wscale) {
+    float m = *absmax;
+    if (!(m > 0.f)) m = 1.f;
+    int e = 0;
+    frexpf(m, &e);                         // m = f * 2^e, f in [0.5, 1)
+    const int s = 14 - e;
+    *wscale = ldexpf(1.f, s);
+    *inv_wscale = ldexpf(1.f, -s);
+}
+
+// weights: w' = (w*scale) * 2^s  ->  fp16 hi / lo
+__global__ void weight_split_kernel(const float *__restrict__ pw, int64_t count, const float *__restrict__ wscale_p,
+                                    __half *__restrict__ hi, __half *__restrict__ lo) {
+    const float wscale = *wscale_p;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        float w = pw[i] * wscale;          // power-of-two scale: exact
+        __half h = __float2half_rn(w);
+        hi[i] = h;
+        lo[i] = __float2half_rn(w - __half2float(h));
+    }
+}
+
+__global__ void absmax_kernel(const float *__restrict__ x, int64_t count, float *__restrict__ out) {
+    float m = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(x[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));   // m >= 0: int order == float order
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D fp16 row-major [rows, cols] tensor, box = box_rows x 64 columns, 128B swizzle
+static int make_tmap_f16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return GSB_ERR_CUDA; }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return GSB_ERR_CUDA; }
+    return GSB_OK;
+}
+
+// Tensor-core packed layout (appended after the fp32 SIMT pack inside the same allocation):
+//   [n_layers][dim*dim] fp16 W_hi | [n_layers][dim*dim] fp16 W_lo | [3][n_layers] float {inv_wscale, wscale, absmax} | flag
+size_t mapping_tc_packed_bytes(int n_layers, int dim) {
+    return align_up((size_t)n_layers * dim * dim * 2, 256) * 2 + align_up((size_t)3 * n_layers * sizeof(float), 256) + 256;
+}
+
+struct TcPackView {
+    __half *w_hi, *w_lo;
+    float *inv_wscale, *wscale, *absmax;
+    unsigned *overflow;
+};
+static TcPackView tc_pack_view(void *base, int n_layers, int dim) {
+    TcPackView v;
+    char *p = reinterpret_cast<char *>(base);
+    size_t wb = align_up((size_t)n_layers * dim * dim * 2, 256);
+    v.w_hi = reinterpret_cast<__half *>(p);
+    v.w_lo = reinterpret_cast<__half *>(p + wb);
+    v.inv_wscale = reinterpret_cast<float *>(p + 2 * wb);
+    v.wscale = v.inv_wscale + n_layers;
+    v.absmax = v.wscale + n_layers;
+    v.overflow = reinterpret_cast<unsigned *>(p + 2 * wb + align_up((size_t)3 * n_layers * sizeof(float), 256));
+    return v;
+}
+
+// Splits the already scale-multiplied fp32 weights `pw` ([n_layers][dim*dim]); stream-ordered, no host sync.
+int mapping_tc_pack(const float *pw, int n_layers, int dim, void *tc_base, cudaStream_t st) {
+    TcPackView v = tc_pack_view(tc_base, n_layers, dim);
+    GSB_CHECK_CUDA(cudaMemsetAsync(v.inv_wscale, 0, (size_t)3 * n_layers * sizeof(float), st));
+    GSB_CHECK_CUDA(cudaMemsetAsync(v.overflow, 0, sizeof(unsigned), st));
+    const int64_t per = (int64_t)dim * dim;
+    for (int l = 0; l < n_layers; ++l) {
+        absmax_kernel<<<64, 256, 0, st>>>(pw + l * per, per, v.absmax + l);
+        GSB_CHECK_LAUNCH();
+        pick_wscale_kernel<<<1, 1, 0, st>>>(v.absmax + l, v.wscale + l, v.inv_wscale + l);
+        GSB_CHECK_LAUNCH();
+        weight_split_kernel<<<256, 256, 0, st>>>(pw + l * per, per, v.wscale + l, v.w_hi + l * per, v.w_lo + l * per);
+        GSB_CHECK_LAUNCH();
+    }
+    return GSB_OK;
+}
+
+// Full mapping network on the tensor cores.  ws: 4 fp16 buffers of n*dim (two hi/lo ping-pong pairs).
+int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim,
+                       const float *d_z, float *d_w, int64_t n, bool pixelnorm, void *ws, cudaStream_t st) {
+    GSB_CHECK_ARG(dim % TC_BLOCK_N == 0 && dim % TC_BLOCK_K == 0, "mapping_forward_tc: dim must be a multiple of 256");
+    GSB_CHECK_ARG(n < (1ll << 31), "mapping_forward_tc: too many rows");
+    TcPackView v = tc_pack_view(tc_base, n_layers, dim);
+    const size_t buf = align_up((size_t)n * dim * 2, 256);
+    __half *a_hi[2] = {reinterpret_cast<__half *>(ws), reinterpret_cast<__half *>((char *)ws + 2 * buf)};
+    __half *a_lo[2] = {reinterpret_cast<__half *>((char *)ws + buf), reinterpret_cast<__half *>((char *)ws + 3 * buf)};
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(mapping_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    pixelnorm_split_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(d_z, a_hi[0], a_lo[0], n, dim, pixelnorm ? 1 : 0,
+                                                                  v.overflow);
+    GSB_CHECK_LAUNCH();
+    const int num_tiles = (int)((n + TC_BLOCK_M - 1) / TC_BLOCK_M) * (dim / TC_BLOCK_N);
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    const int64_t per = (int64_t)dim * dim;
+    for (int l = 0; l < n_layers; ++l) {
+        const int src = l & 1, dst = src ^ 1;
+        CUtensorMap tm_ah, tm_al, tm_wh, tm_wl;
+        if (int r = make_tmap_f16(&tm_ah, a_hi[src], (uint64_t)n, dim, TC_BLOCK_M)) return r;
+        if (int r = make_tmap_f16(&tm_al, a_lo[src], (uint64_t)n, dim, TC_BLOCK_M)) return r;
+        if (int r = make_tmap_f16(&tm_wh, v.w_hi + l * per, dim, dim, TC_BLOCK_N)) return r;
+        if (int r = make_tmap_f16(&tm_wl, v.w_lo + l * per, dim, dim, TC_BLOCK_N)) return r;
+        TcParams p;
+        p.bias = pb + (int64_t)l * dim;
+        const bool last = (l == n_layers - 1);
+        p.out_hi = last ? nullptr : a_hi[dst];
+        p.out_lo = last ? nullptr : a_lo[dst];
+        p.out_f32 = last ? d_w : nullptr;
+        p.overflow = v.overflow;
+        p.inv_wscale = v.inv_wscale + l;
+        p.M = (int)n; p.N_total = dim; p.K = dim;
+        mapping_layer_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_ah, tm_al, tm_wh, tm_wl, p);
+        GSB_CHECK_LAUNCH();
+    }
+    return GSB_OK;
+}
+
+size_t mapping_tc_workspace_bytes(int64_t n, int dim) { return 4 * align_up((size_t)n * dim * 2, 256); }
+
+unsigned *mapping_tc_overflow_flag(void *tc_base, int n_layers, int dim) {
+    return tc_pack_view(tc_base, n_layers, dim).overflow;
+}
+
+}  // namespace gsb

@@ -285,6 +285,8 @@ def compute_arrays(config, instrumented_model):
         zc = torch.from_numpy(Z_comp.reshape(-1, input_dims).astype(np.float32))
         lat_stdev = _native.project_std(samples.contiguous(), zc).cpu().numpy()
 
+    if hasattr(model, "check_numerics"):
+        model.check_numerics()
     arrays = {
         "act_comp": X_comp.astype(np.float32),
         "act_mean": X_global_mean.astype(np.float32),

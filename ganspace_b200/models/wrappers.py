@@ -163,6 +163,10 @@ class StyleGAN2(BaseModel):
             z = self.model.style(z) if out is None else self.model.style.packed().forward(z, out=z)
         return z
 
+    def check_numerics(self):
+        """Raise if a kernel flagged an out-of-range activation since the weights were packed (synchronises)."""
+        self.model.style.packed().check()
+
     def get_max_latents(self):
         return self.model.n_latent
 

@@ -73,11 +73,17 @@ int gsb_mapping_pack(const float *d_weight, const float *d_bias, int n_layers, i
                      void *d_packed, gsb_stream_t stream);
 size_t gsb_mapping_workspace_bytes(int64_t n, int dim);
 /* flags: bit0 = apply PixelNorm first (always set for Generator.style); bit1 = force the SIMT fp32
- * kernels (reference-grade fp32 FMA path used to validate the tensor-core path).
+ * kernels (reference-grade fp32 FMA path used to validate the tensor-core path); default = tcgen05 path
+ * (fp16 hi/lo operand split, 3 MMAs per product, fp32 accumulation in TMEM) when dim % 256 == 0.
  * n_layers == 0 with bit0 set runs PixelNorm alone (d_packed may be NULL). */
 int gsb_mapping_forward(const void *d_packed, int n_layers, int dim, const float *d_z, float *d_w,
                         int64_t n, int flags, void *d_workspace, size_t workspace_bytes,
                         gsb_stream_t stream);
+
+/* Sticky status of the tensor-core path: bit0 = an activation left fp16's range (|x| > 6e4) in some call
+ * since packing, i.e. the fp16 hi/lo operand split was invalid and results must be discarded (re-run with
+ * flags bit1).  This is the one entry point that synchronises (device -> host copy of one word). */
+int gsb_mapping_status(const void *d_packed, int n_layers, int dim, unsigned *h_flags);
 
 /* ------------------------------------------------------------------------------------------------
  * Per-batch sufficient statistics of the incremental PCA (Gram form):

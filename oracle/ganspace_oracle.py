@@ -119,8 +119,8 @@ def pixel_norm(x: np.ndarray) -> np.ndarray:
     return (x * (np.float32(1.0) / np.sqrt(ms))).astype(np.float32)
 
 
-def mapping_forward(z: np.ndarray, weights, biases, lr_mul: float = LR_MLP) -> np.ndarray:
-    """Generator.style: PixelNorm then 8x EqualLinear(activation='fused_lrelu')
+def mapping_forward_np(z: np.ndarray, weights, biases, lr_mul: float = LR_MLP) -> np.ndarray:
+    """Generator.style in plain numpy: PixelNorm then 8x EqualLinear(activation='fused_lrelu')
     (model.py:151-161: F.linear(x, W*scale) ; fused_leaky_relu(out, bias*lr_mul) = sqrt2*lrelu_0.2(out+b))."""
     x = pixel_norm(z)
     for w, b in zip(weights, biases):
@@ -130,6 +130,24 @@ def mapping_forward(z: np.ndarray, weights, biases, lr_mul: float = LR_MLP) -> n
         y = np.where(y >= 0, y, y * np.float32(0.2)).astype(np.float32)
         x = (SQRT2_F32 * y).astype(np.float32)
     return x
+
+
+def mapping_forward(z: np.ndarray, weights, biases, lr_mul: float = LR_MLP) -> np.ndarray:
+    """Same network through the CPU kernels the reference itself calls (torch F.linear / leaky_relu on
+    the host), so that the CPU baseline timed from this oracle spends its time where the reference does.
+    model.py:14-19 (PixelNorm), :151-161 (EqualLinear.forward), op/fused_act.py:86-92 (CPU fallback)."""
+    import math
+    import torch
+    import torch.nn.functional as F
+    with torch.no_grad():
+        x = torch.from_numpy(np.ascontiguousarray(z, dtype=np.float32))
+        x = x * torch.rsqrt(torch.mean(x ** 2, dim=1, keepdim=True) + 1e-8)
+        for w, b in zip(weights, biases):
+            wt, bt = torch.from_numpy(w), torch.from_numpy(b)
+            scale = (1 / math.sqrt(wt.shape[1])) * lr_mul
+            out = F.linear(x, wt * scale)
+            x = (2 ** 0.5) * F.leaky_relu(out + (bt * lr_mul).view(1, -1), negative_slope=0.2)
+        return x.numpy()
 
 
 # --------------------------------------------------------------------------------------------

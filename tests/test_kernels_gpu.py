@@ -68,6 +68,44 @@ def test_mapping_forward_vs_oracle(nat, oracle, mapping_weights, golden, n):
     assert np.max(np.abs(out - ref)) < 2e-5 * max(1.0, np.max(np.abs(ref)))
 
 
+@pytest.mark.parametrize("n", [1, 130, 1000, 10_000])
+def test_mapping_tensor_core_path_vs_simt_and_oracle(nat, oracle, mapping_weights, n):
+    """tcgen05 fp16x3-split path: fp32-grade agreement with the fp32 FMA kernels and the oracle."""
+    ws, bs = mapping_weights
+    pm = nat.PackedMapping(torch.tensor(np.stack(ws)).cuda(), torch.tensor(np.stack(bs)).cuda(), 0.01)
+    z = oracle.standard_normal_f32(77 + n, 512 * n).reshape(n, 512)
+    zt = torch.tensor(z).cuda()
+    simt = pm.forward(zt, force_simt=True).cpu().numpy()
+    tc = pm.forward(zt, force_simt=False).cpu().numpy()
+    pm.check()
+    ref = oracle.mapping_forward(z[:1000], ws, bs)
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(simt[:1000] - ref)) < 2e-5 * scale
+    assert np.max(np.abs(tc[:1000] - ref)) < 2e-5 * scale
+    assert np.max(np.abs(tc - simt)) < 2e-5 * scale
+    # both paths err against an fp64 evaluation by the same order of magnitude
+    def f64(zz):
+        x = zz.astype(np.float64)
+        x = x / np.sqrt(np.mean(x * x, axis=1, keepdims=True) + 1e-8)
+        for w, b in zip(ws, bs):
+            y = x @ (w.astype(np.float64) * np.float64(np.float32((1 / np.sqrt(512)) * 0.01))).T + b * 0.01
+            x = np.sqrt(2.0) * np.where(y >= 0, y, 0.2 * y)
+        return x
+    exact = f64(z[:256])
+    e_tc, e_simt = np.abs(tc[:256] - exact).max(), np.abs(simt[:256] - exact).max()
+    assert e_tc < 4 * e_simt + 1e-6, (e_tc, e_simt)
+
+
+def test_mapping_tensor_core_overflow_is_flagged(nat):
+    rng = np.random.RandomState(1)
+    ws = [(rng.standard_normal((512, 512)) * 1e7).astype(np.float32) for _ in range(2)]
+    bs = [np.zeros(512, np.float32) for _ in range(2)]
+    pm = nat.PackedMapping(torch.tensor(np.stack(ws)).cuda(), torch.tensor(np.stack(bs)).cuda(), 0.01)
+    pm.forward(torch.tensor(rng.standard_normal((64, 512)).astype(np.float32)).cuda(), force_simt=False)
+    with pytest.raises(nat.NativeError, match="fp16 range"):
+        pm.check()
+
+
 def test_mapping_nonzero_bias(nat, oracle):
     rng = np.random.RandomState(0)
     ws = [(rng.standard_normal((512, 512)) * 100).astype(np.float32) for _ in range(3)]
