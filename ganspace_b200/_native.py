@@ -5,6 +5,7 @@ device, this module raises.  torch is used only for device memory and streams.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from pathlib import Path
@@ -296,30 +297,55 @@ def batch_stats(x: torch.Tensor, mean_out: torch.Tensor = None, gram_out: torch.
 
 
 class IPCAChain:
-    """Device-resident IncrementalPCA state + the Gram-form chain step (small-d engine)."""
+    """Device-resident IncrementalPCA state + the Gram-form chain step (small-d engine).
 
-    def __init__(self, d: int, c: int, device):
+    The chain is the sequential part of a run (K dependent eigensolves), so its steps are enqueued on a
+    dedicated high-priority stream: step k waits only for the statistics of group k (an event on the
+    producing stream) and runs while the main stream already generates / reduces the next groups."""
+
+    def __init__(self, d: int, c: int, device, side_stream: bool = True):
         lib = load()
         self.dev = require_cuda(device)
         self.d, self.c = int(d), int(c)
         self.state = torch.empty(lib.gsb_ipca_state_bytes(self.d, self.c), dtype=torch.uint8, device=self.dev)
         self.ws = torch.empty(lib.gsb_ipca_workspace_bytes(self.d, self.c), dtype=torch.uint8, device=self.dev)
         self.n_seen = 0
+        self.stream = None
+        if side_stream and os.environ.get("GANSPACE_B200_CHAIN_STREAM", "1") != "0":
+            with torch.cuda.device(self.dev):
+                self.stream = torch.cuda.Stream(device=self.dev, priority=-1)
         with torch.cuda.device(self.dev):
             _check(lib.gsb_ipca_reset(_ptr(self.state), self.d, self.c, _stream()), "gsb_ipca_reset")
+            if self.stream is not None:
+                self.stream.wait_stream(torch.cuda.current_stream())
 
     def step(self, n_batch: int, mean_b: torch.Tensor, gram_b: torch.Tensor):
         lib = load()
         assert mean_b.dtype == torch.float64 and gram_b.dtype == torch.float64
-        with torch.cuda.device(self.dev), instrument.section("chain"):
-            _check(lib.gsb_ipca_chain_step(_ptr(self.state), self.d, self.c, self.n_seen, int(n_batch),
-                                           _ptr(mean_b), _ptr(gram_b), _ptr(self.ws), self.ws.numel(), _stream()),
-                   "gsb_ipca_chain_step")
-        instrument.count(7)
+        with torch.cuda.device(self.dev):
+            if self.stream is not None:
+                self.stream.wait_stream(torch.cuda.current_stream())      # statistics of this group are ready
+                mean_b.record_stream(self.stream)
+                gram_b.record_stream(self.stream)
+                ctx = torch.cuda.stream(self.stream)
+            else:
+                ctx = contextlib.nullcontext()
+            with ctx, instrument.section("chain"):
+                _check(lib.gsb_ipca_chain_step(_ptr(self.state), self.d, self.c, self.n_seen, int(n_batch),
+                                               _ptr(mean_b), _ptr(gram_b), _ptr(self.ws), self.ws.numel(), _stream()),
+                       "gsb_ipca_chain_step")
+        instrument.count(8)
         self.n_seen += int(n_batch)
+
+    def join(self):
+        """Make the current stream wait for every chain step enqueued so far."""
+        if self.stream is not None:
+            with torch.cuda.device(self.dev):
+                torch.cuda.current_stream().wait_stream(self.stream)
 
     def export(self):
         lib = load()
+        self.join()
         f64 = dict(dtype=torch.float64, device=self.dev)
         out = {
             "components": torch.empty((self.c, self.d), **f64), "singular_values": torch.empty(self.c, **f64),

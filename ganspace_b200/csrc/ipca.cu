@@ -17,6 +17,8 @@
 //   4. backtransform_kernel  applies the reflectors (one warp per eigenvector) and the sign rule.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace gsb {
 
@@ -36,7 +38,7 @@ __host__ __device__ inline StateView state_view(void *p, int d, int c) {
 }
 
 struct Workspace {
-    double *A, *dg, *e, *beta, *Vh, *lam, *Z, *lu, *xch, *evecs;
+    double *A, *dg, *e, *beta, *Vh, *lam, *Z, *lu, *xch, *evecs, *qx;
     unsigned *counter;
     unsigned char *swp;
     size_t bytes;
@@ -57,6 +59,7 @@ static Workspace carve(void *base, int d, int c) {
     w.lu = (double *)take((size_t)5 * d * c * 8);
     w.swp = (unsigned char *)take((size_t)d * c);
     w.xch = (double *)take((size_t)4 * d * 8);
+    w.qx = (double *)take((size_t)2 * 16 * 512 * 8);
     w.counter = (unsigned *)take(256);
     w.bytes = off;
     return w;
@@ -128,13 +131,26 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target)
 // ---------------------------------------------------------------------------------------------
 // Householder tridiagonalisation  A = Q T Q^T,  Q = H_0 H_1 ... H_{n-3},  H_k = I - beta_k v_k v_k^T
 // ---------------------------------------------------------------------------------------------
-constexpr int TRI_THREADS = 256;
+constexpr int TRI_THREADS_GRID = 256;      // global-barrier variant: P = n/8 CTAs
+constexpr int TRI_THREADS_CLUSTER = 512;   // cluster variant: one 16-CTA cluster, hardware barrier
+constexpr int TRI_CLUSTER = 16;
 
-__global__ void __launch_bounds__(TRI_THREADS, 1)
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// CLUSTER = false: any number of co-resident CTAs, software barrier on a global counter.
+// CLUSTER = true : the grid is ONE thread-block cluster (16 CTAs, non-portable size); the per-reflector
+//                  exchange is ordered by barrier.cluster (release/acquire), ~5x cheaper than the atomic
+//                  counter, and the column blocks (n/16 columns = 128 KB for n = 512) stay in shared memory.
+template <bool CLUSTER>
+__global__ void __launch_bounds__(CLUSTER ? TRI_THREADS_CLUSTER : TRI_THREADS_GRID, 1)
 tridiag_kernel(const double *__restrict__ A, int n, double *__restrict__ dg, double *__restrict__ e,
                double *__restrict__ beta, double *__restrict__ Vh, double *__restrict__ xch,
                unsigned *__restrict__ counter) {
     extern __shared__ double smd[];
+    const int TRI_THREADS = blockDim.x;
     const int P = gridDim.x, me = blockIdx.x, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = TRI_THREADS / 32;
     const int ncl = n / P;
@@ -204,8 +220,13 @@ tridiag_kernel(const double *__restrict__ A, int n, double *__restrict__ dg, dou
             }
         }
         // ---- 3. exchange ---------------------------------------------------------------------
-        target += (unsigned)P;
-        grid_barrier(counter, target);
+        if (CLUSTER) {
+            __syncthreads();
+            cluster_barrier();
+        } else {
+            target += (unsigned)P;
+            grid_barrier(counter, target);
+        }
         // ---- 4. w, next pivot column (redundant in every CTA) -------------------------------------
         part = 0.0;
         for (int i = k + 1 + tid; i < n; i += TRI_THREADS) {
@@ -234,73 +255,211 @@ tridiag_kernel(const double *__restrict__ A, int n, double *__restrict__ dg, dou
 }
 
 // ---------------------------------------------------------------------------------------------
-// top-c eigenvalues of the tridiagonal T by 32-way multisection on Sturm counts
+// Register-resident variant of the cluster tridiagonalisation (n <= 512, n % 16 == 0).
+// The shared-memory variants above spend their time on shared-memory bandwidth (every matrix element
+// is read and written once per reflector, plus three vector operands).  Here the CTA's column block
+// lives in REGISTERS: thread (warp w, lane l) owns row i = 16 l + w of the CTA's <= 32 columns
+// j = me + 16 c.  Per reflector a thread applies the pending rank-2 update to its 32 elements with the
+// column operands broadcast from shared memory, the per-column sums are formed by a 31-shuffle
+// transpose-reduce inside each warp and a 16-way add across warps, and all row-indexed vector work
+// (v_i, w_i, next pivot column) is O(1) per thread.
 // ---------------------------------------------------------------------------------------------
-constexpr int BIS_THREADS = 256;
+constexpr int TRR_NC = 32;   // columns per CTA (registers)
+// qx: [2][16][512] doubles of per-CTA partial products (row-permuted so that a warp reads 256 contiguous bytes)
+__global__ void __launch_bounds__(TRI_THREADS_CLUSTER, 1)
+tridiag_reg_kernel(const double *__restrict__ A, int n, double *__restrict__ dg, double *__restrict__ e,
+                   double *__restrict__ beta, double *__restrict__ Vh, double *__restrict__ xch,
+                   double *__restrict__ qx) {
+    __shared__ double vsh[512];                 // v_k by row / column index
+    __shared__ double2 pvw[512];                // pending (v_{k-1}, w_{k-1}) by row / column index
+    __shared__ double red[64];
+    const int me = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nc = n / TRI_CLUSTER;             // active columns of this CTA
+    const int i = 16 * lane + warp;             // own row
+    const bool row_ok = i < n;
+
+    double Areg[TRR_NC];
+#pragma unroll
+    for (int c = 0; c < TRR_NC; ++c) {
+        const int j = me + TRI_CLUSTER * c;
+        Areg[c] = (row_ok && c < nc) ? A[(size_t)j * n + i] : 0.0;      // A[i][j] == A[j][i]
+    }
+    double a_i = row_ok ? A[i] : 0.0;            // pivot column 0 (row 0 of A), own row
+    double pv_i = 0.0, pw_i = 0.0;
+    pvw[tid] = make_double2(0.0, 0.0);
+    if (me == 0 && tid == 0) dg[0] = A[0];
+    __syncthreads();
+
+    for (int k = 0; k <= n - 3; ++k) {
+        const int par = k & 1;
+        double *Rbuf = xch + (size_t)par * n;
+        double *Qbuf = qx + (size_t)par * TRI_CLUSTER * 512;
+        // ---- 1. reflector (redundant in every CTA; one row per thread) ---------------------------
+        if (i == k + 1) red[32] = a_i;
+        const double sigma = block_sum((row_ok && i > k + 1) ? a_i * a_i : 0.0, red);
+        const double x0 = red[32];
+        double alpha, bk, v0;
+        if (sigma == 0.0) {
+            alpha = x0; bk = 0.0; v0 = 0.0;
+        } else {
+            const double nrm = sqrt(x0 * x0 + sigma);
+            alpha = (x0 > 0.0) ? -nrm : nrm;
+            v0 = x0 - alpha;
+            bk = 1.0 / (nrm * (nrm + fabs(x0)));
+        }
+        const double v_i = (!row_ok || i <= k || bk == 0.0) ? 0.0 : ((i == k + 1) ? v0 : a_i);
+        if (row_ok) vsh[i] = v_i;                                // every index < n has exactly one owner
+        __syncthreads();
+        if (me == 0) {
+            if (tid == 0) { e[k] = alpha; beta[k] = bk; }
+            if (tid < n) Vh[(size_t)k * n + tid] = vsh[tid];
+        }
+        // ---- 2. pending rank-2 update + this CTA's share of (A v)_i, row-wise (A is symmetric) ----------
+        // columns j = me + 16 c with j > k are live:  c0 <= c < nc
+        const int c0 = (k >= me) ? ((k - me) / TRI_CLUSTER + 1) : 0;
+        const bool pivot_row = (i == k + 1);
+        double q = 0.0;
+#pragma unroll
+        for (int c = 0; c < TRR_NC; ++c) {
+            if ((unsigned)(c - c0) < (unsigned)(nc - c0)) {
+                const int j = me + TRI_CLUSTER * c;
+                const double2 pj = pvw[j];                       // broadcast: (pv_j, pw_j)
+                const double x = Areg[c] - pv_i * pj.y - pw_i * pj.x;
+                Areg[c] = x;
+                q += x * vsh[j];
+                if (pivot_row) __stcg(&Rbuf[j], x);              // pivot row of A^(k)
+            }
+        }
+        __stcg(&Qbuf[me * 512 + tid], q);                        // row i's partial, permuted index = tid
+        // ---- 3. exchange -------------------------------------------------------------------------
+        cluster_barrier();
+        // ---- 4. p, w, next pivot column (one row per thread) ------------------------------------------
+        const bool act = row_ok && i > k;
+        double p_i = 0.0;
+        if (act) {
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < TRI_CLUSTER; r += 2) {
+                t0 += __ldcg(&Qbuf[r * 512 + tid]);
+                t1 += __ldcg(&Qbuf[(r + 1) * 512 + tid]);
+            }
+            p_i = bk * (t0 + t1);
+        }
+        const double r_i = act ? __ldcg(&Rbuf[i]) : 0.0;
+        const double ptv = block_sum(p_i * v_i, red);
+        const double w_i = p_i - 0.5 * bk * ptv * v_i;
+        if (i == k + 1) { red[33] = v_i; red[34] = w_i; }
+        if (row_ok) pvw[i] = make_double2(v_i, w_i);
+        __syncthreads();
+        const double vk1 = red[33], wk1 = red[34];
+        a_i = act ? (r_i - vk1 * w_i - wk1 * v_i) : 0.0;
+        pv_i = v_i; pw_i = w_i;
+        if (me == 0 && i == k + 1) dg[k + 1] = a_i;
+    }
+    // last 2x2 block
+    if (me == 0 && i == n - 1) { e[n - 2] = a_i; e[n - 1] = 0.0; beta[n - 2] = 0.0; beta[n - 1] = 0.0; }
+    if (me == (n - 1) % TRI_CLUSTER && i == n - 1) {
+        const int cl = (n - 1) / TRI_CLUSTER;
+        double last = 0.0;
+#pragma unroll
+        for (int c = 0; c < TRR_NC; ++c) if (c == cl) last = Areg[c];
+        dg[n - 1] = last - 2.0 * pv_i * pw_i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// top-c eigenvalues of the tridiagonal T: 128-way multisection on Sturm counts, one CTA per eigenvalue.
+// The count uses the division-free three-term recurrence  p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}
+// (q_i = p_i / p_{i-1} are the LDL^T pivots whose negative signs are counted); T is pre-scaled by a power
+// of two so that |d - x| <= 2, e^2 <= 1, and (p_i, p_{i-1}) is renormalised by an exact power of two every
+// 8 steps.  The dependent chain is one DFMA per row instead of a division.
+// ---------------------------------------------------------------------------------------------
+constexpr int BIS_THREADS = 128;
 __global__ void __launch_bounds__(BIS_THREADS)
 bisect_kernel(const double *__restrict__ dg, const double *__restrict__ e, int n, int c,
               double *__restrict__ lam) {
     extern __shared__ double smd[];
     double *sd = smd, *se2 = smd + n, *red = se2 + n;   // red[64]
+    __shared__ double s_x[BIS_THREADS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double gl = 1e300, gu = -1e300, emax = 0.0;
+    double gl = 1e300, gu = -1e300;
     for (int i = tid; i < n; i += BIS_THREADS) {
         double di = dg[i];
         double el = (i > 0) ? fabs(e[i - 1]) : 0.0, er = (i < n - 1) ? fabs(e[i]) : 0.0;
-        sd[i] = di;
-        se2[i] = (i < n - 1) ? e[i] * e[i] : 0.0;
         gl = fmin(gl, di - el - er);
         gu = fmax(gu, di + el + er);
-        emax = fmax(emax, er * er);
     }
-    // block min / max via shared scratch
     for (int o = 16; o > 0; o >>= 1) {
         gl = fmin(gl, __shfl_xor_sync(0xffffffffu, gl, o));
         gu = fmax(gu, __shfl_xor_sync(0xffffffffu, gu, o));
-        emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
     }
-    if (lane == 0) { red[warp] = gl; red[8 + warp] = gu; red[16 + warp] = emax; }
+    if (lane == 0) { red[warp] = gl; red[8 + warp] = gu; }
     __syncthreads();
-    gl = red[0]; gu = red[8]; emax = red[16];
-    for (int q = 1; q < BIS_THREADS / 32; ++q) {
-        gl = fmin(gl, red[q]); gu = fmax(gu, red[8 + q]); emax = fmax(emax, red[16 + q]);
+    gl = red[0]; gu = red[8];
+    for (int q = 1; q < BIS_THREADS / 32; ++q) { gl = fmin(gl, red[q]); gu = fmax(gu, red[8 + q]); }
+    const double eps = 2.220446049250313e-16;
+    double tnorm = fmax(fabs(gl), fabs(gu));
+    if (!(tnorm > 0.0)) tnorm = 1.0;
+    int ex;
+    frexp(tnorm, &ex);
+    const double sc = ldexp(1.0, -ex);               // power of two: scaled spectrum within [-1, 1]
+    for (int i = tid; i < n; i += BIS_THREADS) {
+        sd[i] = dg[i] * sc;
+        double es = (i < n - 1) ? e[i] * sc : 0.0;
+        se2[i] = es * es;
     }
-    const double eps = 2.220446049250313e-16, safemin = 2.2250738585072014e-308;
-    const double pivmin = safemin * fmax(1.0, emax);
-    const double tnorm = fmax(fabs(gl), fabs(gu));
-    const double margin = 2.0 * tnorm * eps * n + 2.0 * pivmin;
-    const int t = blockIdx.x * (BIS_THREADS / 32) + warp;   // t-th largest
-    if (t >= c) return;
-    const int m = n - 1 - t;                                 // ascending index
-    double lo = gl - margin, hi = gu + margin;
-    for (int it = 0; it < 16; ++it) {
+    __syncthreads();
+    const int t = blockIdx.x;                         // t-th largest
+    const int m = n - 1 - t;                          // ascending index
+    const double margin = 4.0 * eps * n;
+    double lo = gl * sc - margin, hi = gu * sc + margin;
+    for (int it = 0; it < 12; ++it) {
         const double width = hi - lo;
-        const double x = lo + width * ((double)(lane + 1) / 33.0);
-        // Sturm count: number of eigenvalues < x
+        const double x = lo + width * ((double)(tid + 1) / (double)(BIS_THREADS + 1));
+        // number of eigenvalues < x  =  number of sign changes p_{i-1} -> p_i  (sign bits of the high
+        // words; an exact zero is taken as positive and shows up as a change one row later)
         int cnt = 0;
-        double q = sd[0] - x;
-        if (fabs(q) <= pivmin) q = -pivmin;
-        cnt += (q < 0.0);
-        for (int i = 1; i < n; ++i) {
-            q = sd[i] - x - se2[i - 1] / q;
-            if (fabs(q) <= pivmin) q = -pivmin;
-            cnt += (q < 0.0);
+        double pm = 1.0, pc = sd[0] - x;              // p_{-1}, p_0
+        cnt += (unsigned)__double2hiint(pc) >> 31;
+        for (int i0 = 1; i0 < n; i0 += 8) {
+            const int i1 = (i0 + 8 < n) ? i0 + 8 : n;
+#pragma unroll 8
+            for (int i = i0; i < i1; ++i) {
+                const double pn = (sd[i] - x) * pc - se2[i - 1] * pm;
+                cnt += (unsigned)(__double2hiint(pn) ^ __double2hiint(pc)) >> 31;
+                pm = pc; pc = pn;
+            }
+            // renormalise by an exact power of two (keeps signs and the ratio)
+            const double mag = fmax(fabs(pc), fabs(pm));
+            const int eb = ((__double2hiint(mag) >> 20) & 0x7ff) - 1023;
+            if (eb > 200 || eb < -200) {
+                const double f = (mag > 0.0) ? __hiloint2double((1023 - eb) << 20, 0) : 1.0;
+                pc *= f; pm *= f;
+                if (mag == 0.0) { pc = 1e-300; pm = 0.0; }
+            }
         }
+        s_x[tid] = x;
+        __syncthreads();
+        // first probe with count >= m+1 bounds the eigenvalue from above
         unsigned mask = __ballot_sync(0xffffffffu, cnt >= m + 1);
-        int f = mask ? (__ffs(mask) - 1) : 32;
-        double xhi = __shfl_sync(0xffffffffu, x, f & 31);
-        double xlo = __shfl_sync(0xffffffffu, x, (f > 0 ? f - 1 : 0));
-        double nhi = (f < 32) ? xhi : hi;
-        double nlo = (f > 0) ? xlo : lo;
+        if (lane == 0) reinterpret_cast<unsigned *>(red)[warp] = mask;
+        __syncthreads();
+        int f = BIS_THREADS;
+        for (int q = BIS_THREADS / 32 - 1; q >= 0; --q) {
+            unsigned mq = reinterpret_cast<unsigned *>(red)[q];
+            if (mq) f = q * 32 + __ffs(mq) - 1;
+        }
+        const double nhi = (f < BIS_THREADS) ? s_x[f] : hi;
+        const double nlo = (f > 0) ? s_x[f - 1] : lo;
+        __syncthreads();
         hi = nhi; lo = nlo;
-        if (hi - lo <= 2.0 * eps * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin || hi - lo >= width) break;
+        if (hi - lo <= 2.0 * eps * fmax(fabs(lo), fabs(hi)) + 1e-300 || hi - lo >= width) break;
     }
-    if (lane == 0) lam[t] = 0.5 * (lo + hi);
+    if (tid == 0) lam[t] = 0.5 * (lo + hi) / sc;
 }
 
 // ---------------------------------------------------------------------------------------------
-// eigenvectors of T: inverse iteration on the partially pivoted LU of T - lambda I (one thread each)
-// scratch arrays are [i][t] so that the threads of a warp touch consecutive addresses
+// eigenvectors of T: inverse iteration on the partially pivoted LU of T - lambda I
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double hash_unit(unsigned i, unsigned t) {
     unsigned h = i * 2654435761u ^ (t + 1u) * 40503u;
@@ -308,73 +467,99 @@ __device__ __forceinline__ double hash_unit(unsigned i, unsigned t) {
     return ((double)(h & 0xffffffu) / 8388608.0) - 1.0;   // [-1, 1)
 }
 
-__global__ void invit_kernel(const double *__restrict__ dg, const double *__restrict__ e,
-                             const double *__restrict__ lam, int n, int c, double *__restrict__ lu,
-                             unsigned char *__restrict__ swp, double *__restrict__ Z) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per eigenvector; the pivoted LU (stored as reciprocal pivots so that the solves are FMA chains)
+// and the iterate live in shared memory.  Lane 0 walks the three sequential recurrences, all lanes share
+// the O(n) parallel parts.
+constexpr int IV_WARPS = 4;
+__global__ void __launch_bounds__(IV_WARPS * 32)
+invit_kernel(const double *__restrict__ dg, const double *__restrict__ e, const double *__restrict__ lam, int n,
+             int c, double *__restrict__ Z) {
+    extern __shared__ double smd[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * IV_WARPS + warp;
     if (t >= c) return;
-    const size_t cs = (size_t)c;
-    double *u0 = lu, *u1 = lu + (size_t)n * cs, *u2 = lu + 2 * (size_t)n * cs, *ml = lu + 3 * (size_t)n * cs,
-           *xb = lu + 4 * (size_t)n * cs;
+    double *u0i = smd + (size_t)warp * (5 * (size_t)n + (size_t)(n + 7) / 8);   // 1/pivot
+    double *u1 = u0i + n, *u2 = u1 + n, *ml = u2 + n, *xb = ml + n;
+    unsigned char *swp = reinterpret_cast<unsigned char *>(xb + n);
     const double lambda = lam[t];
-    // scale for tiny pivots: eps * ||T||_1-ish
     double tn = 0.0;
-    for (int i = 0; i < n; ++i) tn = fmax(tn, fabs(dg[i]) + ((i < n - 1) ? fabs(e[i]) : 0.0) + ((i > 0) ? fabs(e[i - 1]) : 0.0));
+    for (int i = lane; i < n; i += 32)
+        tn = fmax(tn, fabs(dg[i]) + ((i < n - 1) ? fabs(e[i]) : 0.0) + ((i > 0) ? fabs(e[i - 1]) : 0.0));
+    for (int o = 16; o > 0; o >>= 1) tn = fmax(tn, __shfl_xor_sync(0xffffffffu, tn, o));
     const double tiny = fmax(2.220446049250313e-16 * tn, 1e-300);
-
-    double p = dg[0] - lambda, q = (n > 1) ? e[0] : 0.0;
-    for (int i = 0; i < n - 1; ++i) {
-        const double sub = e[i];
-        const double dn = dg[i + 1] - lambda;
-        const double sn = (i + 1 < n - 1) ? e[i + 1] : 0.0;
-        const size_t o = (size_t)i * cs + t;
-        if (fabs(p) >= fabs(sub)) {
-            if (fabs(p) < tiny) p = (p < 0.0) ? -tiny : tiny;
-            const double mult = sub / p;
-            u0[o] = p; u1[o] = q; u2[o] = 0.0; ml[o] = mult; swp[o] = 0;
-            p = dn - mult * q;
-            q = sn;
-        } else {
-            const double mult = p / sub;
-            u0[o] = sub; u1[o] = dn; u2[o] = sn; ml[o] = mult; swp[o] = 1;
-            p = q - mult * dn;
-            q = -mult * sn;
-        }
+    // stage T - lambda I:  u1 <- diagonal, u2 <- off-diagonal (overwritten by the factorisation)
+    for (int i = lane; i < n; i += 32) {
+        u1[i] = dg[i] - lambda;
+        u2[i] = (i < n - 1) ? e[i] : 0.0;
+        xb[i] = hash_unit((unsigned)i, (unsigned)t);
     }
-    if (fabs(p) < tiny) p = (p < 0.0) ? -tiny : tiny;
-    u0[(size_t)(n - 1) * cs + t] = p;
-
-    for (int i = 0; i < n; ++i) xb[(size_t)i * cs + t] = hash_unit((unsigned)i, (unsigned)t);
-    for (int iter = 0; iter < 3; ++iter) {
-        // forward: apply the row operations to b
-        double bi = xb[t];
+    __syncwarp();
+    if (lane == 0) {
+        double p = u1[0], q = u2[0];
         for (int i = 0; i < n - 1; ++i) {
-            const size_t o = (size_t)i * cs + t;
-            double bn = xb[o + cs];
-            if (swp[o]) { double tmp = bi; bi = bn; bn = tmp; }
-            xb[o] = bi;
-            bi = bn - ml[o] * bi;
+            const double sub = u2[i];
+            const double dn = u1[i + 1];
+            const double sn = u2[i + 1];            // 0 for the last row
+            if (fabs(p) >= fabs(sub)) {
+                if (fabs(p) < tiny) p = (p < 0.0) ? -tiny : tiny;
+                const double pinv = 1.0 / p;
+                const double mult = sub * pinv;
+                u0i[i] = pinv; u1[i] = q; u2[i] = 0.0; ml[i] = mult; swp[i] = 0;
+                p = dn - mult * q;
+                q = sn;
+            } else {
+                const double sinv = 1.0 / sub;
+                const double mult = p * sinv;
+                u0i[i] = sinv; u1[i] = dn; u2[i] = sn; ml[i] = mult; swp[i] = 1;
+                p = q - mult * dn;
+                q = -mult * sn;
+            }
         }
-        xb[(size_t)(n - 1) * cs + t] = bi;
-        // backward
-        double x2 = 0.0, x1 = 0.0, amax = 0.0;
-        for (int i = n - 1; i >= 0; --i) {
-            const size_t o = (size_t)i * cs + t;
-            double r = xb[o];
-            if (i < n - 1) r -= u1[o] * x1;
-            if (i < n - 2) r -= u2[o] * x2;
-            double x = r / u0[o];
-            xb[o] = x;
-            x2 = x1; x1 = x;
-            amax = fmax(amax, fabs(x));
-        }
-        // normalise: max-abs first (overflow guard), then 2-norm
-        double inv = 1.0 / amax, ss = 0.0;
-        for (int i = 0; i < n; ++i) { double x = xb[(size_t)i * cs + t] * inv; ss += x * x; }
-        inv = inv / sqrt(ss);
-        for (int i = 0; i < n; ++i) xb[(size_t)i * cs + t] *= inv;
+        if (fabs(p) < tiny) p = (p < 0.0) ? -tiny : tiny;
+        u0i[n - 1] = 1.0 / p; u1[n - 1] = 0.0; u2[n - 1] = 0.0;
     }
-    for (int i = 0; i < n; ++i) Z[(size_t)t * n + i] = xb[(size_t)i * cs + t];
+    __syncwarp();
+    // fold the reciprocal pivots into the upper factor: x_i = c0_i - c1_i x_{i+1} - c2_i x_{i+2}, so the
+    // dependent chain of the back substitution is one DFMA per row
+    for (int i = lane; i < n; i += 32) { u1[i] *= u0i[i]; u2[i] *= u0i[i]; }
+    __syncwarp();
+    for (int iter = 0; iter < 2; ++iter) {
+        if (lane == 0) {
+            double bi = xb[0], bn = xb[1];
+            for (int i = 0; i < n - 1; ++i) {             // forward: replay the row operations
+                const double bnn = (i + 2 < n) ? xb[i + 2] : 0.0;   // prefetch off the dependent chain
+                double lo_ = bi, hi_ = bn;
+                if (swp[i]) { lo_ = bn; hi_ = bi; }
+                xb[i] = lo_;
+                bi = hi_ - ml[i] * lo_;
+                bn = bnn;
+            }
+            xb[n - 1] = bi;
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) xb[i] *= u0i[i];   // c0
+        __syncwarp();
+        if (lane == 0) {
+            double x1 = 0.0, x2 = 0.0;
+            for (int i = n - 1; i >= 0; --i) {            // backward: U x = b
+                const double t0 = xb[i] - u2[i] * x2;     // x2 is one step old: off the chain
+                const double x = t0 - u1[i] * x1;
+                xb[i] = x;
+                x2 = x1; x1 = x;
+            }
+        }
+        __syncwarp();
+        double amax = 0.0;
+        for (int i = lane; i < n; i += 32) amax = fmax(amax, fabs(xb[i]));
+        for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        double inv = 1.0 / amax, ss = 0.0;
+        for (int i = lane; i < n; i += 32) { double x = xb[i] * inv; ss += x * x; }
+        ss = warp_sum(ss);
+        inv = inv / sqrt(ss);
+        for (int i = lane; i < n; i += 32) xb[i] *= inv;
+        __syncwarp();
+    }
+    for (int i = lane; i < n; i += 32) Z[(size_t)t * n + i] = xb[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -444,41 +629,109 @@ cluster_orth_kernel(const double *__restrict__ lam, const double *__restrict__ d
 // ---------------------------------------------------------------------------------------------
 // eigenvectors of A:  x = H_0 H_1 ... H_{n-3} z ; then the svd_flip sign rule (largest |.| entry > 0)
 // ---------------------------------------------------------------------------------------------
-constexpr int BT_WARPS = 4;
+// One CTA = 8 warps = 8 eigenvectors, each held in its warp's registers (NR = n/32 doubles per lane); the
+// reflectors stream from L2 through a cp.async ring shared by the 8 warps (BT_DEPTH pairs in flight), two
+// reflectors per barrier, so the ~510 dependent steps are paced by the per-step dot/axpy.
+constexpr int BT_WARPS = 8;
+constexpr int BT_DEPTH = 4;      // ring slots, each holding a PAIR of reflectors
+template <int NR>
 __global__ void __launch_bounds__(BT_WARPS * 32)
 backtransform_kernel(const double *__restrict__ Z, const double *__restrict__ Vh,
                      const double *__restrict__ beta, int n, int c, double *__restrict__ out) {
     extern __shared__ double smd[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = blockIdx.x * BT_WARPS + warp;
-    if (t >= c) return;
-    double *z = smd + (size_t)warp * n;
-    for (int i = lane; i < n; i += 32) z[i] = Z[(size_t)t * n + i];
-    __syncwarp();
-    for (int k = n - 3; k >= 0; --k) {
-        const double bk = beta[k];
-        if (bk == 0.0) continue;
-        const double *vk = Vh + (size_t)k * n;
-        double s = 0.0;
-        for (int i = k + 1 + lane; i < n; i += 32) s += vk[i] * z[i];
-        s = warp_sum(s) * bk;
-        for (int i = k + 1 + lane; i < n; i += 32) z[i] -= s * vk[i];
-        __syncwarp();
+    const bool active = t < c;
+    double *ring = smd;                                    // [BT_DEPTH][2][n]
+    double z[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int i = lane + 32 * r;
+        z[r] = (active && i < n) ? Z[(size_t)t * n + i] : 0.0;
     }
+    const int nchunk = n;                                  // 16-byte chunks per reflector pair (2 * n/2)
+    const int npairs = (n - 2 + 1) / 2;                    // reflectors k = n-3 .. 0, processed (k, k-1)
+    auto prefetch = [&](int pidx) {                        // pair pidx holds reflectors k = n-3-2*pidx and k-1
+        if (pidx < npairs) {
+            const int k = n - 3 - 2 * pidx;
+            double *dst = ring + (size_t)(pidx % BT_DEPTH) * 2 * n;
+            for (int ch = tid; ch < nchunk; ch += BT_WARPS * 32) {
+                const int which = ch / (n / 2), off = ch % (n / 2);
+                const int kk = k - which;
+                if (kk >= 0) {
+                    unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (size_t)which * n + 2 * off);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(Vh + (size_t)kk * n + 2 * off)
+                                 : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int j = 0; j < BT_DEPTH - 1; ++j) prefetch(j);
+    for (int pidx = 0; pidx < npairs; ++pidx) {
+        prefetch(pidx + BT_DEPTH - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(BT_DEPTH - 1) : "memory");
+        __syncthreads();
+        const double *base = ring + (size_t)(pidx % BT_DEPTH) * 2 * n;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const int k = n - 3 - 2 * pidx - which;
+            if (k < 0) break;
+            const double bk = beta[k];
+            if (bk == 0.0) continue;
+            const double *vk = base + (size_t)which * n;
+            double vr[NR], s = 0.0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int i = lane + 32 * r;
+                vr[r] = (i > k && i < n) ? vk[i] : 0.0;
+                s += vr[r] * z[r];
+            }
+            s = warp_sum(s) * bk;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) z[r] -= s * vr[r];
+        }
+        __syncthreads();                                   // the slot is refilled by the next prefetch
+    }
+    if (!active) return;
     // argmax |z| (first index on ties, as np.argmax)
     double best = -1.0;
     int bi = 0;
-    for (int i = lane; i < n; i += 32) {
-        double az = fabs(z[i]);
-        if (az > best) { best = az; bi = i; }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int i = lane + 32 * r;
+        const double az = fabs(z[r]);
+        if (i < n && az > best) { best = az; bi = i; }
     }
+    double bval = 0.0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) if (lane + 32 * r == bi) bval = z[r];
     for (int o = 16; o > 0; o >>= 1) {
         double ob = __shfl_xor_sync(0xffffffffu, best, o);
         int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        double ov = __shfl_xor_sync(0xffffffffu, bval, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; bval = ov; }
     }
-    const double sgn = (z[bi] < 0.0) ? -1.0 : 1.0;
-    for (int i = lane; i < n; i += 32) out[(size_t)t * n + i] = sgn * z[i];
+    const double sgn = (bval < 0.0) ? -1.0 : 1.0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int i = lane + 32 * r;
+        if (i < n) out[(size_t)t * n + i] = sgn * z[r];
+    }
+}
+
+template <int NR>
+static int launch_backtransform(const double *Z, const double *Vh, const double *beta, int d, int c, double *evecs,
+                                cudaStream_t st) {
+    const size_t smem = (size_t)BT_DEPTH * 2 * d * sizeof(double);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(backtransform_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    backtransform_kernel<NR><<<(c + BT_WARPS - 1) / BT_WARPS, BT_WARPS * 32, smem, st>>>(Z, Vh, beta, d, c, evecs);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -533,34 +786,96 @@ __global__ void export_kernel(const double *hdr, const double *mean, const doubl
 
 // ---------------------------------------------------------------------------------------------
 static int eig_top(const Workspace &w, int d, int c, double *evals, double *evecs, cudaStream_t st) {
-    // P CTAs, 8 columns each (n % 8 == 0); all must be co-resident for the grid barrier
-    int P = d / 8;
-    while (P > 128) P /= 2;
-    GSB_CHECK_ARG(d % P == 0, "sym_eig: d=%d not divisible by P=%d", d, P);
-    const int ncl = d / P;
-    const size_t tri_smem = ((size_t)ncl * d + 5 * (size_t)d + 64) * sizeof(double);
-    GSB_CHECK_ARG(tri_smem <= 200 * 1024, "sym_eig: d=%d too large for the small-d engine", d);
-    static size_t tri_smem_set = 0;
-    if (tri_smem > tri_smem_set) {
-        GSB_CHECK_CUDA(cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)tri_smem));
-        tri_smem_set = tri_smem;
+    // Preferred: one 16-CTA cluster (hardware barrier) when the column blocks fit in shared memory.
+    static int cluster_ok = -1;     // -1 unknown, 0 unavailable, 1 usable
+    const size_t cl_smem = ((size_t)(d / TRI_CLUSTER) * d + 5 * (size_t)d + 64) * sizeof(double);
+    bool use_cluster = (d % TRI_CLUSTER == 0) && cl_smem <= 227 * 1024;
+    if (use_cluster && cluster_ok == -1) {
+        const char *env = getenv("GANSPACE_B200_TRIDIAG");
+        cluster_ok = (env && strcmp(env, "grid") == 0) ? 0 : 1;
+        if (cluster_ok) {
+            if (cudaFuncSetAttribute(tridiag_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                cudaFuncSetAttribute(tridiag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+                cluster_ok = 0;
+                (void)cudaGetLastError();
+            }
+        }
+        if (cluster_ok) {
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(TRI_CLUSTER); q.blockDim = dim3(TRI_THREADS_CLUSTER); q.dynamicSmemBytes = cl_smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = TRI_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            q.attrs = at; q.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, tridiag_kernel<true>, &q) != cudaSuccess || nclusters < 1) {
+                cluster_ok = 0;
+                (void)cudaGetLastError();
+            }
+        }
     }
-    GSB_CHECK_CUDA(cudaMemsetAsync(w.counter, 0, 256, st));
-    tridiag_kernel<<<P, TRI_THREADS, tri_smem, st>>>(w.A, d, w.dg, w.e, w.beta, w.Vh, w.xch, w.counter);
-    GSB_CHECK_LAUNCH();
+    if (use_cluster && cluster_ok == 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(TRI_CLUSTER); cfg.blockDim = dim3(TRI_THREADS_CLUSTER);
+        cfg.dynamicSmemBytes = cl_smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = TRI_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        static int reg_variant = -1;
+        if (reg_variant == -1) {
+            const char *env = getenv("GANSPACE_B200_TRIDIAG");
+            reg_variant = (env && strcmp(env, "smem") == 0) ? 0 : 1;
+            if (reg_variant &&
+                cudaFuncSetAttribute(tridiag_reg_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+                reg_variant = 0;
+                (void)cudaGetLastError();
+            }
+        }
+        if (reg_variant && d <= 512) {
+            cfg.dynamicSmemBytes = 0;
+            GSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tridiag_reg_kernel, (const double *)w.A, d, w.dg, w.e, w.beta, w.Vh,
+                                              w.xch, w.qx));
+        } else {
+            GSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tridiag_kernel<true>, (const double *)w.A, d, w.dg, w.e, w.beta,
+                                              w.Vh, w.xch, w.counter));
+        }
+    } else {
+        // P CTAs, 8 columns each (n % 8 == 0); all must be co-resident for the software grid barrier
+        int P = d / 8;
+        while (P > 128) P /= 2;
+        GSB_CHECK_ARG(d % P == 0, "sym_eig: d=%d not divisible by P=%d", d, P);
+        const int ncl = d / P;
+        const size_t tri_smem = ((size_t)ncl * d + 5 * (size_t)d + 64) * sizeof(double);
+        GSB_CHECK_ARG(tri_smem <= 200 * 1024, "sym_eig: d=%d too large for the small-d engine", d);
+        static size_t tri_smem_set = 0;
+        if (tri_smem > tri_smem_set) {
+            GSB_CHECK_CUDA(cudaFuncSetAttribute(tridiag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)tri_smem));
+            tri_smem_set = tri_smem;
+        }
+        GSB_CHECK_CUDA(cudaMemsetAsync(w.counter, 0, 256, st));
+        tridiag_kernel<false><<<P, TRI_THREADS_GRID, tri_smem, st>>>(w.A, d, w.dg, w.e, w.beta, w.Vh, w.xch, w.counter);
+        GSB_CHECK_LAUNCH();
+    }
     const size_t bis_smem = (2 * (size_t)d + 64) * sizeof(double);
-    bisect_kernel<<<(c + 7) / 8, BIS_THREADS, bis_smem, st>>>(w.dg, w.e, d, c, evals);
+    bisect_kernel<<<c, BIS_THREADS, bis_smem, st>>>(w.dg, w.e, d, c, evals);
     GSB_CHECK_LAUNCH();
-    invit_kernel<<<(c + 31) / 32, 32, 0, st>>>(w.dg, w.e, evals, d, c, w.lu, w.swp, w.Z);
+    const size_t iv_smem = (size_t)IV_WARPS * (5 * (size_t)d + (size_t)(d + 7) / 8) * sizeof(double);
+    static size_t iv_smem_set = 0;
+    if (iv_smem > iv_smem_set) {
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(invit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iv_smem));
+        iv_smem_set = iv_smem;
+    }
+    invit_kernel<<<(c + IV_WARPS - 1) / IV_WARPS, IV_WARPS * 32, iv_smem, st>>>(w.dg, w.e, evals, d, c, w.Z);
     GSB_CHECK_LAUNCH();
     const size_t co_smem = ((size_t)d + c + 64) * sizeof(double) + (size_t)c * sizeof(int);
     cluster_orth_kernel<<<1, CO_THREADS, co_smem, st>>>(evals, w.dg, w.e, d, c, w.Z);
     GSB_CHECK_LAUNCH();
-    const size_t bt_smem = (size_t)BT_WARPS * d * sizeof(double);
-    backtransform_kernel<<<(c + BT_WARPS - 1) / BT_WARPS, BT_WARPS * 32, bt_smem, st>>>(w.Z, w.Vh, w.beta, d, c,
-                                                                                      evecs);
-    GSB_CHECK_LAUNCH();
+    if (d <= 128) { if (int r = launch_backtransform<4>(w.Z, w.Vh, w.beta, d, c, evecs, st)) return r; }
+    else if (d <= 256) { if (int r = launch_backtransform<8>(w.Z, w.Vh, w.beta, d, c, evecs, st)) return r; }
+    else if (d <= 512) { if (int r = launch_backtransform<16>(w.Z, w.Vh, w.beta, d, c, evecs, st)) return r; }
+    else { if (int r = launch_backtransform<32>(w.Z, w.Vh, w.beta, d, c, evecs, st)) return r; }
     return GSB_OK;
 }
 

@@ -31,12 +31,16 @@ def _run(n, b, c, use_w, outclass="ffhq", seed=None):
     return out, path.name
 
 
+AUX_TOL = 1e-4         # means / stdevs: fp32-grade.  The tcgen05 mapping path carries a systematic -1.3e-5 relative
+                       # scale (the tensor core truncates when aligning addends); the fp32 FMA path is at 1e-7.
+
+
 def _check(cmp, lat_tol=COS_TOL):
     assert cmp["min_signed_cos"] >= COS_TOL, cmp
     assert cmp["max_abs_dvar_ratio"] <= RATIO_TOL, cmp
     assert cmp["min_lat_signed_cos"] >= lat_tol, cmp
-    assert cmp["act_mean_rel"] < 1e-5 and cmp["act_stdev_rel"] < 1e-4, cmp
-    assert cmp["lat_stdev_rel"] < 1e-3 and cmp["random_stdevs_rel"] < 1e-3, cmp
+    assert cmp["act_mean_rel"] < AUX_TOL and cmp["act_stdev_rel"] < AUX_TOL, cmp
+    assert cmp["lat_stdev_rel"] < AUX_TOL and cmp["random_stdevs_rel"] < AUX_TOL, cmp
 
 
 def test_config1_vs_reference_golden(golden, oracle):
