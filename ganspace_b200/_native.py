@@ -28,6 +28,7 @@ SIGNATURES = {
     "gsb_mapping_workspace_bytes": (_Z, [_L, _I]),
     "gsb_mapping_forward": (_I, [_P, _I, _I, _P, _P, _L, _I, _P, _Z, _P]),
     "gsb_mapping_status": (_I, [_P, _I, _I, _P]),
+    "gsb_linear_forward": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P, _Z, _P]),
     "gsb_batch_stats_workspace_bytes": (_Z, [_L, _I]),
     "gsb_batch_stats": (_I, [_P, _L, _I, _L, _P, _P, _P, _Z, _P]),
     "gsb_ipca_state_bytes": (_Z, [_I, _I]),
@@ -261,6 +262,23 @@ class PackedMapping:
                                            flags, _ptr(ws), ws.numel(), _stream()), "gsb_mapping_forward")
         instrument.count(self.n_layers + (1 if pixelnorm else 0))
         return out.reshape(z.shape)
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor = None, lrelu: bool = False) -> torch.Tensor:
+    """y = x @ w.T (+ bias) in the fp32 FMA GEMM kernel; x [n,K], w [N,K] (N % 128 == 0, K % 16 == 0)."""
+    lib = load()
+    assert x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and x.shape[-1] == w.shape[1]
+    x2 = x.reshape(-1, x.shape[-1]).contiguous()
+    w = w.contiguous()
+    n, K = x2.shape
+    N = w.shape[0]
+    y = torch.empty((n, N), dtype=torch.float32, device=x.device)
+    ws = scratch.get("linear", 4 * N, x.device)
+    with torch.cuda.device(x.device), instrument.section("linear"):
+        _check(lib.gsb_linear_forward(_ptr(x2), _ptr(w), _ptr(bias.contiguous() if bias is not None else None), _ptr(y),
+                                      n, N, K, 1 if lrelu else 0, _ptr(ws), ws.numel(), _stream()), "gsb_linear_forward")
+    instrument.count(1)
+    return y.reshape(*x.shape[:-1], N)
 
 
 def mapping_pixelnorm(z: torch.Tensor) -> torch.Tensor:

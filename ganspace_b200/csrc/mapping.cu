@@ -243,3 +243,29 @@ extern "C" int gsb_mapping_status(const void *d_packed, int n_layers, int dim, u
                               cudaMemcpyDeviceToHost));
     return GSB_OK;
 }
+
+// Generic affine layer  y[n,N] = x[n,K] * W[N,K]^T + bias[N]  (bias may be NULL), optional sqrt2*lrelu.
+//   replaces  nn.Linear / F.linear call sites of the path outside the mapping network, e.g. BigGAN's
+//   generator.gen_z (biggan model.py:211-212,232; spectral norm folded into W by the caller).
+extern "C" int gsb_linear_forward(const float *d_x, const float *d_w, const float *d_bias, float *d_y, int64_t n,
+                                  int N, int K, int flags, void *d_workspace, size_t workspace_bytes,
+                                  gsb_stream_t stream) {
+    GSB_CHECK_ARG(d_x && d_w && d_y, "linear_forward: null pointer");
+    GSB_CHECK_ARG(n >= 0 && N > 0 && K > 0 && N % 128 == 0 && K % 16 == 0, "linear_forward: need N%%128==0, K%%16==0 (N=%d K=%d)", N, K);
+    if (n == 0) return GSB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float *bias = d_bias;
+    if (!bias) {
+        if (!d_workspace || workspace_bytes < (size_t)N * sizeof(float)) {
+            gsb::set_error("linear_forward: workspace of N floats needed when bias is NULL");
+            return GSB_ERR_WORKSPACE;
+        }
+        GSB_CHECK_CUDA(cudaMemsetAsync(d_workspace, 0, (size_t)N * sizeof(float), st));
+        bias = reinterpret_cast<const float *>(d_workspace);
+    }
+    dim3 grid((unsigned)((n + gsb::BM - 1) / gsb::BM), N / gsb::BN);
+    if (flags & 1) gsb::sgemm_tn_bias_act_kernel<true><<<grid, gsb::SGEMM_THREADS, 0, st>>>(d_x, d_w, bias, d_y, n, N, K);
+    else gsb::sgemm_tn_bias_act_kernel<false><<<grid, gsb::SGEMM_THREADS, 0, st>>>(d_x, d_w, bias, d_y, n, N, K);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}

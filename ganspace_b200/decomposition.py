@@ -14,8 +14,8 @@ batch through host memory and runs sklearn's IncrementalPCA on the CPU; here
 so activations never leave HBM; the host only draws the seeds (NumPy global state, as the reference
 does) and receives the final components.
 
-Multi-GPU (one process per GPU, torch.distributed initialised): partial_fit group k is owned by rank
-k mod world; every rank computes the statistics of its groups into slot k of a [K, d*d+d] buffer, ONE
+Multi-GPU (one process per GPU, torch.distributed initialised): the partial_fit groups are split into
+contiguous blocks, one per rank; every rank computes the statistics of its groups into slot k of a [K, d*d+d] buffer, ONE
 all-reduce exchanges them, and every rank replays the K-step chain in the reference's order -- the
 result does not depend on the world size.
 """
@@ -99,7 +99,9 @@ def _sample_batches(model, Bsz, seeds, out=None):
 
 
 # Solve for directions in latent space that match PCs in activation space (reference :77-139)
-def linreg_lstsq(comp_np, mean_np, stdev_np, inst, config):
+def linreg_lstsq(comp_np, mean_np, stdev_np, inst, config, affine=None):
+    """``affine``: when the hooked layer is affine in the latent (models/biggan.py AffineLayer), comp/mean are
+    given in its r-dimensional coordinates and the projections run there: (act-mean).comp^T == (y-ybar).comp_y^T."""
     print("Performing least squares regression", flush=True)
     torch.manual_seed(SEED_LINREG)
     np.random.seed(SEED_LINREG)
@@ -124,9 +126,12 @@ def linreg_lstsq(comp_np, mean_np, stdev_np, inst, config):
         z_all = _sample_batches(model, B, [seeds[i] for i in idx])
         for j in range(len(idx)):
             z = z_all[j * B:(j + 1) * B]
-            with torch.no_grad():
-                model.partial_forward(z, config.layer)
-            act = inst.retained_features()[config.layer].reshape(B, -1)
+            if affine is not None:
+                act = affine.coords(z.reshape(B, -1))
+            else:
+                with torch.no_grad():
+                    model.partial_forward(z, config.layer)
+                act = inst.retained_features()[config.layer].reshape(B, -1)
             acc.accumulate(act.contiguous(), comp, mean, stdev, z.reshape(B, -1).contiguous())
     if live:
         import torch.distributed as dist
@@ -137,12 +142,12 @@ def linreg_lstsq(comp_np, mean_np, stdev_np, inst, config):
     return M_t.cpu().numpy()[:n_comp, :], Z_mean.cpu().numpy().reshape(1, -1)
 
 
-def regression(comp, mean, stdev, inst, config):
+def regression(comp, mean, stdev, inst, config, affine=None):
     M = np.dot(comp, comp.T)
     if not np.allclose(M, np.identity(M.shape[0])):
         det = np.linalg.det(M)
         print(f"WARNING: Computed basis is not orthonormal (determinant={det})")
-    return linreg_lstsq(comp, mean, stdev, inst, config)
+    return linreg_lstsq(comp, mean, stdev, inst, config, affine=affine)
 
 
 def compute(config, dump_name, instrumented_model):
@@ -196,6 +201,11 @@ def compute_arrays(config, instrumented_model):
     input_dims = int(inst.model.get_latent_dims())
 
     config.components = min(config.components, sample_dims)
+    # layers that are affine in the latent expose a thin factorisation act = (z R^T) Q^T + offset; the PCA then
+    # runs on the r-dimensional coordinates and is lifted through the isometry Q at the end (models/biggan.py)
+    affine = model.affine_layer(layer_key) if hasattr(model, "affine_layer") else None
+    if affine is not None and config.components > affine.rank:
+        raise NotImplementedError(f"components={config.components} exceeds the rank {affine.rank} of layer {layer_key}")
     transformer = get_estimator(config.estimator, config.components, config.sparsity, device=device)
     if not transformer.batch_support:
         raise RuntimeError("only batched estimators run on the device path")
@@ -214,23 +224,26 @@ def compute_arrays(config, instrumented_model):
 
     # ---- Phase B: per-group statistics + merge chain (:239-265) ------------------------------------
     K = pl.K
-    d = sample_dims
+    d = affine.rank if affine is not None else sample_dims
     groups_per_chunk = max(1, int(LATENT_CHUNK_BYTES // max(1, NB * input_dims * 4)))
     slots = torch.zeros((K, _plan.slot_width(d)), dtype=torch.float64, device=device) if live else None
     X = None
     tr = transformer.transformer
     for c0 in range(0, K, groups_per_chunk):
         mine = _plan.groups_to_process(pl, rank, world, c0, min(c0 + groups_per_chunk, K))
-        for run in _plan.contiguous_runs(mine):          # contiguous groups share generated batches
-            row0, row1 = pl.group_rows(run[0])[0], pl.group_rows(run[-1])[1]
-            b0, b1 = pl.batches_covering(row0, row1)
-            lat = _sample_batches(model, B, seeds[b0:b1])
-            lat = lat.reshape(lat.shape[0], -1)
+        runs = _plan.contiguous_runs(mine)
+        # every sample_latent call this rank needs for the chunk, generated by ONE launch (one CTA per seed)
+        needed, offsets = _plan.batch_slots(pl, runs)
+        lat = _sample_batches(model, B, [seeds[b] for b in needed])
+        lat = lat.reshape(lat.shape[0], -1)
+        for run, off in zip(runs, offsets):
             for k in run:
-                gi = pl.group_rows(k)[0]
-                rows = lat[gi - b0 * B: gi - b0 * B + NB]
+                r = off + (k - run[0]) * NB
+                rows = lat[r:r + NB]
                 if samples_are_latents:
                     X = rows
+                elif affine is not None:
+                    X = affine.coords(rows)
                 else:
                     X = torch.empty((NB, d), dtype=torch.float32, device=device)
                     for mb in range(0, NB, B):
@@ -241,21 +254,34 @@ def compute_arrays(config, instrumented_model):
                         space_left = min(B, NB - mb)
                         X[mb:mb + space_left] = batch[:space_left]
                 if live:
-                    if _plan.owner(k, world) == rank:
+                    if _plan.owner(k, world, K) == rank:
                         n_b, mean_b, gram_b = tr.batch_stats(X)
                         slots[k, :d * d] = gram_b.reshape(-1)
                         slots[k, d * d:] = mean_b
                 elif not transformer.fit_partial(X):
                     break
-            del lat    # X (a view of the last group when samples_are_latents) keeps its storage alive
+        del lat    # X (a view of the last group when samples_are_latents) keeps its storage alive
     if live:
         import torch.distributed as dist
         dist.all_reduce(slots)                         # the run's single exchange of PCA statistics
         _plan.replay(pl, slots, d, lambda nb, m, g: tr.merge(nb, m.contiguous(), g.contiguous()))
 
-    X_global_mean = tr.mean_.reshape((1, sample_dims))
     X_comp, X_stdev, X_var_ratio = transformer.get_components()
     X_comp = np.array(X_comp, copy=True)
+    mean_dev = tr.device_attributes()["mean"]
+    if affine is None:
+        X_global_mean = tr.mean_.reshape((1, sample_dims))
+        Y_comp, Y_mean = X_comp, X_global_mean
+    else:
+        # lift through the isometry: components = components_y Q^T (svd_flip's sign rule is applied on the lifted
+        # rows, as sklearn would on the full activations), mean = mean_y Q^T + offset
+        lifted = affine.lift_rows(torch.from_numpy(X_comp).to(device))
+        idx = torch.argmax(lifted.abs(), dim=1)
+        signs = torch.sign(lifted[torch.arange(lifted.shape[0], device=device), idx])
+        Y_comp = X_comp * signs.cpu().numpy()[:, None]
+        Y_mean = tr.mean_.reshape((1, d))
+        X_comp = (lifted * signs[:, None]).cpu().numpy()
+        X_global_mean = (affine.lift_rows(mean_dev[None, :]) + affine.offset[None, :]).cpu().numpy()
 
     assert X_comp.shape[1] == sample_dims and X_comp.shape[0] == config.components \
         and X_global_mean.shape[1] == sample_dims and X_stdev.shape[0] == config.components, "Invalid shape"
@@ -264,15 +290,17 @@ def compute_arrays(config, instrumented_model):
         Z_comp = X_comp
         Z_global_mean = X_global_mean
     else:
-        Z_comp, Z_global_mean = regression(X_comp, X_global_mean, X_stdev, inst, config)
+        Z_comp, Z_global_mean = regression(Y_comp, Y_mean, X_stdev, inst, config, affine=affine)
 
     Z_comp /= np.linalg.norm(Z_comp, axis=-1, keepdims=True)
 
     # random projections of the last group's buffer, centred on the global mean (:289-291,312-316)
     random_dirs = get_random_dirs(config.components, int(np.prod(sample_shape)))
     n_rand_samples = min(5000, X.shape[0])
-    mean_dev = tr.device_attributes()["mean"]
-    X_stdev_random = _native.project_std(X[:n_rand_samples], torch.from_numpy(random_dirs), sub=mean_dev).cpu().numpy()
+    dirs_dev = torch.from_numpy(random_dirs).to(device)
+    if affine is not None:                                  # dirs . (x - mean) == (dirs Q) . (y - ybar)
+        dirs_dev = _native.linear(dirs_dev, affine.Q.T.float().contiguous())
+    X_stdev_random = _native.project_std(X[:n_rand_samples], dirs_dev, sub=mean_dev).cpu().numpy()
 
     X_comp = X_comp.reshape(-1, *sample_shape)
     X_global_mean = X_global_mean.reshape(sample_shape)

@@ -80,6 +80,14 @@ int gsb_mapping_forward(const void *d_packed, int n_layers, int dim, const float
                         int64_t n, int flags, void *d_workspace, size_t workspace_bytes,
                         gsb_stream_t stream);
 
+/* Generic affine layer y[n,N] = x[n,K] W[N,K]^T + bias[N] in fp32 FMA (bias may be NULL: pass a workspace of
+ * N floats); flags bit0 = apply sqrt2*leaky_relu_0.2.  Needs N % 128 == 0, K % 16 == 0.
+ *   replaces  the nn.Linear call sites of the path outside the mapping network: BigGAN generator.gen_z
+ *   (biggan model.py:211-212,232, spectral norm folded into W by the caller) and the small projections of the
+ *   low-rank activation path. */
+int gsb_linear_forward(const float *d_x, const float *d_w, const float *d_bias, float *d_y, int64_t n, int N,
+                       int K, int flags, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
+
 /* Sticky status of the tensor-core path: bit0 = an activation left fp16's range (|x| > 6e4) in some call
  * since packing, i.e. the fp16 hi/lo operand split was invalid and results must be discarded (re-run with
  * flags bit1).  This is the one entry point that synchronises (device -> host copy of one word). */

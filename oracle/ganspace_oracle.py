@@ -300,27 +300,28 @@ class _GlobalSeeds:
         return s
 
 
-def compute_stylegan2_style(weights, biases, n: int, B: int, c: int, use_w: bool, seed=None,
-                            ipca: str = "svd", return_aux: bool = False):
-    """Restated decomposition.compute (:150-341) for model=StyleGAN2, layer='style', estimator='ipca'.
+def compute_path(sample, activate, latent_dims: int, feat_dims: int, n: int, B: int, c: int,
+                 samples_are_latents: bool, seed=None, ipca: str = "svd", use_w: bool = False, return_aux=False):
+    """Restated decomposition.compute (:150-341) for estimator='ipca'.
+        sample(seed, B)   -> one model.sample_latent(B) call (latents [B, latent_dims], float32)
+        activate(latents) -> the hooked layer's activations flattened to [B, feat_dims]
     ``ipca``: 'svd' = sklearn-form partial_fit restatement, 'gram' = Gram-chain restatement."""
-    d = 512
+    d = feat_dims
     c = min(c, d)                                                    # :191
     N, NB, n_lat, K = plan(n, B, c)
     seeds = _GlobalSeeds(seed or SEED_SAMPLING)                      # :226-227
 
-    # Phase A (:232-236): one sample_latent(B) per micro-batch; W-space applies the mapping here
-    latents = np.zeros((n_lat, d), np.float32)
+    # Phase A (:232-236): one sample_latent(B) per micro-batch
+    latents = np.zeros((n_lat, latent_dims), np.float32)
     for i in range(n_lat // B):
-        z = standard_normal_f32(seeds.next(), d * B).reshape(B, d)
-        latents[i * B:(i + 1) * B] = mapping_forward(z, weights, biases) if use_w else z
+        latents[i * B:(i + 1) * B] = sample(seeds.next(), B)
 
     # Phase B (:239-265)
     st = IPCAState(c)
     X = None
     for gi in range(0, N, NB):
         rows = latents[gi:gi + NB]
-        X = (rows if use_w else mapping_forward(rows, weights, biases)).astype(np.float32).copy()
+        X = (rows if samples_are_latents else activate(rows)).astype(np.float32).copy()
         if ipca == "svd":
             ipca_partial_fit(st, X)
         else:
@@ -332,12 +333,12 @@ def compute_stylegan2_style(weights, biases, n: int, B: int, c: int, use_w: bool
     X_stdev = np.sqrt(st.explained_variance)
     X_var_ratio = st.explained_variance_ratio
 
-    if use_w:                                                        # samples_are_latents (:239,297-299)
+    if samples_are_latents:                                          # :297-299
         Z_comp, Z_mean = X_comp, X_global_mean
     else:                                                            # :301-305 -> linreg_lstsq :77-139
-        Z_comp, Z_mean = linreg_style(weights, biases, X_comp, X_global_mean, X_stdev, n, B)
+        Z_comp, Z_mean = linreg(sample, activate, latent_dims, X_comp, X_global_mean, X_stdev, n, B)
     Z_comp = Z_comp / np.linalg.norm(Z_comp, axis=-1, keepdims=True)  # :308
-    if use_w:
+    if samples_are_latents:
         X_comp = Z_comp                                              # same ndarray in the reference
 
     random_dirs = get_random_dirs(c, d)                              # :312
@@ -345,31 +346,28 @@ def compute_stylegan2_style(weights, biases, n: int, B: int, c: int, use_w: bool
     X_stdev_random = np.dot(random_dirs, X[:n_rand].T).std(axis=1)   # :313-316
 
     lat_stdev = np.ones_like(X_stdev)                                # :325
-    aux = {}
     if use_w:                                                        # :326-329
-        z = standard_normal_f32(seeds.next(), d * 5000).reshape(5000, d)
-        samples = mapping_forward(z, weights, biases)
-        coords = np.dot(Z_comp.reshape(-1, d), samples.T)
+        samples = sample(seeds.next(), 5000)
+        coords = np.dot(Z_comp.reshape(-1, latent_dims), samples.T)
         lat_stdev = coords.std(axis=1)
 
     out = {                                                          # :331-341
         "act_comp": X_comp.reshape(-1, 1, d).astype(np.float32),
         "act_mean": X_global_mean.reshape(1, d).astype(np.float32),
         "act_stdev": X_stdev.astype(np.float32),
-        "lat_comp": Z_comp.reshape(-1, 1, d).astype(np.float32),
-        "lat_mean": np.asarray(Z_mean).reshape(1, d).astype(np.float32),
+        "lat_comp": Z_comp.reshape(-1, 1, latent_dims).astype(np.float32),
+        "lat_mean": np.asarray(Z_mean).reshape(1, latent_dims).astype(np.float32),
         "lat_stdev": lat_stdev.astype(np.float32),
         "var_ratio": X_var_ratio.astype(np.float32),
         "random_stdevs": X_stdev_random.astype(np.float32),
     }
     if return_aux:
-        aux.update(state=st, N=N, NB=NB, n_lat=n_lat, K=K)
-        return out, aux
+        return out, dict(state=st, N=N, NB=NB, n_lat=n_lat, K=K)
     return out
 
 
-def linreg_style(weights, biases, comp, mean, stdev, n: int, B: int):
-    """decomposition.py:77-139 for layer='style' in Z space: regress latent z on scaled PC coordinates."""
+def linreg(sample, activate, latent_dims, comp, mean, stdev, n: int, B: int):
+    """decomposition.py:77-139: regress the latent on the scaled PC coordinates of the activations."""
     import scipy.linalg
     seeds = _GlobalSeeds(SEED_LINREG)                                # :80-81
     seeds.next()   # :88 get_latent_dims() -> get_latent_shape() -> sample_latent(1) eats one global draw
@@ -378,15 +376,74 @@ def linreg_style(weights, biases, comp, mean, stdev, n: int, B: int):
     stdev32 = stdev.astype(np.float32)
     n_samp = max(10_000, n) // B * B                                 # :87
     A = np.zeros((n_samp, comp.shape[0]), np.float32)
-    Z = np.zeros((n_samp, 512), np.float32)
+    Z = np.zeros((n_samp, latent_dims), np.float32)
     for i in range(n_samp // B):                                     # :115-126
-        z = standard_normal_f32(seeds.next(), 512 * B).reshape(B, 512)
-        act = mapping_forward(z, weights, biases) - mean32
+        z = sample(seeds.next(), B)
+        act = activate(z) - mean32
         coords = act @ comp32.T
         A[i * B:(i + 1) * B] = coords / stdev32
         Z[i * B:(i + 1) * B] = z
     M_t = scipy.linalg.lstsq(A, Z, lapack_driver="gelsd")[0]        # :133
     return M_t[:comp.shape[0], :].astype(np.float64), np.mean(Z, axis=0, keepdims=True)
+
+
+def compute_stylegan2_style(weights, biases, n: int, B: int, c: int, use_w: bool, seed=None,
+                            ipca: str = "svd", return_aux: bool = False):
+    """model=StyleGAN2, layer='style' (wrappers.py:167-179,194-222): W space (--use_w: sample_latent applies the
+    mapping, samples are the latents) or Z space (activations = mapping(z), regression back to z)."""
+    mapping = lambda z: mapping_forward(z, weights, biases)
+    normals = lambda s, B_: standard_normal_f32(s, 512 * B_).reshape(B_, 512)
+    if use_w:
+        sample = lambda s, B_: mapping(normals(s, B_))
+        return compute_path(sample, None, 512, 512, n, B, c, True, seed=seed, ipca=ipca, use_w=True,
+                            return_aux=return_aux)
+    return compute_path(normals, mapping, 512, 512, n, B, c, False, seed=seed, ipca=ipca, return_aux=return_aux)
+
+
+# --------------------------------------------------------------------------------------------
+# BigGAN generator.gen_z  (wrappers.py:562-569,611-648; biggan utils.py:21-33, model.py:51-52,211-212,291)
+# --------------------------------------------------------------------------------------------
+def truncated_noise_sample(seed: int, batch_size: int, dim_z: int = 128, truncation: float = 1.0) -> np.ndarray:
+    """biggan utils.py:21-33: truncnorm.rvs(-2, 2, size, random_state=RandomState(seed)).astype(f32)*truncation.
+    SciPy's truncnorm draws RandomState.uniform and applies the inverse CDF ndtri(Phi(a) + u (Phi(b)-Phi(a)))."""
+    from scipy.special import ndtr, ndtri
+    u = random_sample_f64(seed, batch_size * dim_z)
+    pa, pb = ndtr(-2.0), ndtr(2.0)
+    vals = ndtri(pa + u * (pb - pa)).astype(np.float32).reshape(batch_size, dim_z)
+    return (np.float32(truncation) * vals).astype(np.float32)
+
+
+def biggan_genz_random_init(seed: int = 4321, z_dim: int = 128, out_features: int = 4 * 4 * 16 * 128, eps: float = 1e-4):
+    """Random-init tensors of the reference's BigGAN that gen_z depends on: torch.manual_seed(seed) followed
+    by BigGAN(config) creates embeddings (nn.Linear(1000,128,bias=False)) and then
+    generator.gen_z = spectral_norm(nn.Linear(256, 32768)) before anything else (biggan model.py:288-293,204-212)."""
+    import torch
+    from torch import nn
+    torch.manual_seed(seed)
+    emb = nn.Linear(1000, z_dim, bias=False)
+    lin = nn.utils.spectral_norm(nn.Linear(2 * z_dim, out_features), eps=eps)
+    w = lin.weight_orig.detach()
+    sigma = torch.dot(lin.weight_u, torch.mv(w, lin.weight_v))      # eval mode: no power iteration
+    return {"w_eff": (w / sigma).numpy(), "bias": lin.bias.detach().numpy(), "emb": emb.weight.detach().numpy(),
+            "weight_orig": w.numpy(), "u": lin.weight_u.numpy(), "v": lin.weight_v.numpy()}
+
+
+def genz_forward(z: np.ndarray, params, class_idx: int = 248) -> np.ndarray:
+    """cond = cat(z, embeddings(one_hot)); act = gen_z(cond)  (wrappers.py:627-636), through torch's CPU F.linear."""
+    import torch
+    import torch.nn.functional as F
+    with torch.no_grad():
+        zt = torch.from_numpy(np.ascontiguousarray(z, dtype=np.float32))
+        embed = torch.from_numpy(params["emb"][:, class_idx]).unsqueeze(0).expand(zt.shape[0], -1)
+        cond = torch.cat((zt, embed), dim=1)
+        return F.linear(cond, torch.from_numpy(params["w_eff"]), torch.from_numpy(params["bias"])).numpy()
+
+
+def compute_biggan_genz(params, n: int, B: int, c: int, class_idx: int = 248, seed=None, ipca: str = "svd"):
+    """model=BigGAN-512, layer='generator.gen_z' (BASELINE.json config 4)."""
+    sample = lambda s, B_: truncated_noise_sample(s, B_)
+    activate = lambda z: genz_forward(z, params, class_idx)
+    return compute_path(sample, activate, 128, params["w_eff"].shape[0], n, B, c, False, seed=seed, ipca=ipca)
 
 
 # --------------------------------------------------------------------------------------------

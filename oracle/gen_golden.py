@@ -129,6 +129,45 @@ def main():
     np.savez_compressed(OUT / "ipca_chain_d96_c12.npz", X=np.stack(Xs), param_str=np.array(est.get_param_str()),
                         **chain)
 
+    # ---- G6: BigGAN-512 husky, layer=generator.gen_z (config-4 shape, small N), random-init -------------
+    from models import biggan
+    import models.wrappers as mw
+    one_hot = lambda names: biggan.one_hot_from_int([248])          # 'husky' = ImageNet class 248 (no WordNet here)
+    biggan.one_hot_from_names = one_hot
+    mw.biggan.one_hot_from_names = one_hot
+    deep512 = [(False, 16, 16), (True, 16, 16), (False, 16, 16), (True, 16, 8), (False, 8, 8), (True, 8, 8),
+               (False, 8, 8), (True, 8, 4), (False, 4, 4), (True, 4, 2), (False, 2, 2), (True, 2, 1),
+               (False, 1, 1), (True, 1, 1)]
+
+    class RandInitBigGAN(wrappers.BigGAN):
+        def load_model(self, name):
+            torch.manual_seed(4321)
+            cfg = biggan.BigGANConfig(output_dim=512, layers=deep512, attention_layer_position=8)
+            self.model = biggan.BigGAN(cfg).to(self.device)
+
+    bm = RandInitBigGAN(dev, 512, "husky")
+    binst = wrappers.get_instrumented_model("BigGAN-512", "husky", "generator.gen_z", dev, model=bm)
+    bcfg = Config(model="BigGAN-512", layer="generator.gen_z", output_class="husky", estimator="ipca",
+                  n=4_000, batch_size=1_000, components=16)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = decomposition.get_or_compute(bcfg, binst, force_recompute=True,
+                                            submit_config=SimpleNamespace(run_dir=tmp, run_dir_root=tmp))
+        with np.load(path) as data:
+            out6 = {k: data[k].copy() for k in data.files}
+        name6 = path.name
+    np.savez_compressed(OUT / "c4s_biggan512_husky_genz_n4000_b1000_c16.npz", dump_name=np.array(name6), **out6)
+    gz = bm.model.generator.gen_z
+    zs = bm.sample_latent(8, seed=11)
+    with torch.no_grad():
+        bm.partial_forward(zs, "generator.gen_z")
+    act = binst.retained_features()["generator.gen_z"]
+    np.savez_compressed(OUT / "biggan_known_answers.npz", z=zs.numpy(), act=act.numpy(),
+                        weight_orig_sum=np.array(float(gz.weight_orig.double().sum())),
+                        weight_orig_head=gz.weight_orig[:4, :6].detach().numpy(),
+                        bias_head=gz.bias[:8].detach().numpy(), u_head=gz.weight_u[:8].numpy(), v_head=gz.weight_v[:8].numpy(),
+                        emb_head=bm.model.embeddings.weight[:4, :6].detach().numpy(),
+                        trunc_seed5=biggan.truncated_noise_sample(batch_size=4, seed=5))
+
     # ---- report oracle-vs-reference (also asserted by tests/test_oracle_golden.py) -----------------
     ws, bs = orc.mapping_random_init(1234)
     for i in range(8):

@@ -84,11 +84,21 @@ def test_sharding_partitions_groups():
     from ganspace_b200 import plan
     p = plan.make_plan(1_000_000, 10_000, 80)
     for world in (1, 2, 4, 8):
-        owned = [[k for k in plan.groups_to_process(p, r, world) if plan.owner(k, world) == r] for r in range(world)]
+        owned = [[k for k in plan.groups_to_process(p, r, world) if plan.owner(k, world, p.K) == r] for r in range(world)]
         assert sorted(sum(owned, [])) == list(range(p.K))
         for r in range(world):
             assert p.K - 1 in plan.groups_to_process(p, r, world)
     assert plan.contiguous_runs([0, 1, 2, 5, 6, 9]) == [[0, 1, 2], [5, 6], [9]]
+    # a rank's groups need one contiguous set of sample_latent calls (+ the final group's)
+    p2 = plan.make_plan(5_000, 700, 20)          # ragged: B does not divide NB
+    for world in (1, 2, 3):
+        for r in range(world):
+            runs = plan.contiguous_runs(plan.groups_to_process(p2, r, world))
+            needed, offs = plan.batch_slots(p2, runs)
+            assert needed == sorted(set(needed)) and max(needed) < p2.n_calls
+            for run, off in zip(runs, offs):
+                r0 = p2.group_rows(run[0])[0]
+                assert needed[off // p2.B] * p2.B + off % p2.B == r0
 
 
 def test_estimator_surface_and_cache_name():

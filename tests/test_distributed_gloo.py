@@ -41,7 +41,7 @@ def _worker(rank, world, port, out_path):
     touched = plan.groups_to_process(pl, rank, world)
     assert pl.K - 1 in touched
     for k in touched:
-        if plan.owner(k, world) != rank:
+        if plan.owner(k, world, pl.K) != rank:
             continue
         n_b, m, G = orc.batch_stats(data[k])
         slots[k, :d * d] = torch.from_numpy(G.reshape(-1))

@@ -52,3 +52,28 @@ def test_compute_restatement_vs_reference(oracle, golden, mapping_weights, name,
         assert cmp[k] < 1e-5, (k, cmp)
     for k in out:
         assert out[k].shape == g[k].shape and out[k].dtype == g[k].dtype, k
+
+
+def test_biggan_genz_known_answers(oracle, golden):
+    g = golden("biggan_known_answers.npz")
+    p = oracle.biggan_genz_random_init(4321)
+    assert np.isclose(float(p["weight_orig"].astype(np.float64).sum()), float(g["weight_orig_sum"]))
+    assert np.array_equal(p["weight_orig"][:4, :6], g["weight_orig_head"])
+    assert np.array_equal(p["bias"][:8], g["bias_head"]) and np.array_equal(p["emb"][:4, :6], g["emb_head"])
+    assert np.array_equal(p["u"][:8], g["u_head"]) and np.array_equal(p["v"][:8], g["v_head"])
+    assert np.max(np.abs(oracle.truncated_noise_sample(5, 4) - g["trunc_seed5"])) < 1e-6
+    assert np.max(np.abs(oracle.truncated_noise_sample(11, 8) - g["z"])) < 1e-6
+    act = oracle.genz_forward(g["z"], p)
+    assert np.max(np.abs(act - g["act"])) < 1e-5
+
+
+def test_biggan_genz_compute_restatement_vs_reference(oracle, golden):
+    g = golden("c4s_biggan512_husky_genz_n4000_b1000_c16.npz")
+    out = oracle.compute_biggan_genz(oracle.biggan_genz_random_init(4321), 4_000, 1_000, 16)
+    cmp = oracle.compare_npz(out, g)
+    assert cmp["min_signed_cos"] > 1 - 1e-5 and cmp["min_lat_signed_cos"] > 1 - 1e-4, cmp
+    assert cmp["max_abs_dvar_ratio"] < 1e-5, cmp
+    for k in ("act_mean_rel", "act_stdev_rel", "lat_stdev_rel", "random_stdevs_rel"):
+        assert cmp[k] < 1e-4, (k, cmp)
+    for k in out:
+        assert out[k].shape == g[k].shape and out[k].dtype == g[k].dtype, k
