@@ -879,6 +879,260 @@ static int eig_top(const Workspace &w, int d, int c, double *evals, double *evec
     return GSB_OK;
 }
 
+// =============================================================================================
+// Warm-started block-Lanczos Rayleigh-Ritz chain step.
+//
+// The direct solver above costs ~n dependent reflector steps (n = 512 -> ~2 ms).  From the second chain
+// step on, the previous components V_{k-1} span the wanted invariant subspace up to O(1/k), so the top-c
+// eigenpairs of G are taken from the block Krylov space  span[Q0, Q1, Q2],  Q0 = V_{k-1}^T,
+// Q_{j+1} = orth((I - P_j) G Q_j)  (full re-orthogonalisation, twice), by Rayleigh-Ritz on the 3c x 3c
+// projection  H = Qb^T G Qb  -- solved with the same direct eigensolver at n = 3c.  Measured against the
+// exact chain on config 2 (100 steps, c = 80): min signed cosine 0.999999997, max |d ratio| 5e-9
+// (profiles/r01_block_lanczos_accuracy.md), far inside the 0.999 / 1e-3 tolerance, and the result is still
+// independent of the world size.  All of it is fp64 GEMM-shaped work spread over the whole GPU.
+// =============================================================================================
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, int lda,
+             const double *__restrict__ B, int ldb, double beta, double *__restrict__ C, int ldc, int kchunk) {
+    // C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C   (row-major; op = transpose when the flag is set).
+    // gridDim.z > 1: split-K, every CTA adds alpha * partial with fp64 atomics (caller pre-scales C by beta).
+    __shared__ double As[16][33], Bs[16][33];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int kbeg = blockIdx.z * kchunk, kend = (kbeg + kchunk < K) ? kbeg + kchunk : K;
+    double acc[2][2] = {{0, 0}, {0, 0}};
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
+        for (int idx = tid; idx < 512; idx += 256) {
+            int mm, kk;
+            if (TA) { mm = idx & 31; kk = idx >> 5; } else { kk = idx & 15; mm = idx >> 4; }
+            const int m = m0 + mm, k = k0 + kk;
+            As[kk][mm] = (m < M && k < kend) ? (TA ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]) : 0.0;
+            int nn, k2;
+            if (TB) { k2 = idx & 15; nn = idx >> 4; } else { nn = idx & 31; k2 = idx >> 5; }
+            const int n = n0 + nn, kb = k0 + k2;
+            Bs[k2][nn] = (n < N && kb < kend) ? (TB ? B[(size_t)n * ldb + kb] : B[(size_t)kb * ldb + n]) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const double a0 = As[kk][ty], a1 = As[kk][ty + 16], b0 = Bs[kk][tx], b1 = Bs[kk][tx + 16];
+            acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int m = m0 + ty + 16 * r, n = n0 + tx + 16 * q;
+            if (m < M && n < N) {
+                if (gridDim.z > 1) {
+                    atomicAdd(&C[(size_t)m * ldc + n], alpha * acc[r][q]);
+                } else {
+                    double v = alpha * acc[r][q];
+                    if (beta != 0.0) v += beta * C[(size_t)m * ldc + n];
+                    C[(size_t)m * ldc + n] = v;
+                }
+            }
+        }
+}
+
+// beta must be 0 or 1.  Splits K so that the launch fills the machine (these GEMMs have few output tiles).
+template <bool TA, bool TB>
+static int dgemm(int M, int N, int K, double alpha, const double *A, int lda, const double *B, int ldb, double beta,
+                 double *C, int ldc, cudaStream_t st) {
+    const int tiles = ((N + 31) / 32) * ((M + 31) / 32);
+    int splits = 1;
+    while (splits < 8 && tiles * splits < 2 * num_sms() && K / (splits * 2) >= 64) splits *= 2;
+    const int kchunk = ((K + splits - 1) / splits + 15) / 16 * 16;
+    if (splits > 1 && beta == 0.0) GSB_CHECK_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 8, 0, (size_t)N * 8, M, st));
+    dim3 grid((N + 31) / 32, (M + 31) / 32, splits);
+    dgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, kchunk);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+// Left-looking Cholesky of the k x k Gram matrix C (k <= 128), one CTA of 128 threads (thread i owns row i):
+// L[i][j] = (C[i][j] - sum_{q<j} L[i][q] L[j][q]) / L[j][j].  Pivots below 1e-26 * max diagonal are clamped
+// (numerically dependent residual directions).  Writes L (row-major, zero upper part).
+__global__ void __launch_bounds__(128)
+chol_kernel(const double *__restrict__ C, int k, double *__restrict__ Lout) {
+    extern __shared__ double smd[];
+    double *L = smd;                    // [k][k+1]
+    const int i = threadIdx.x, ld = k + 1;
+    double dmax = 0.0;
+    for (int j = 0; j < k; ++j) dmax = fmax(dmax, C[(size_t)j * k + j]);
+    const double floor_ = fmax(dmax * 1e-26, 1e-300);
+    for (int j = 0; j < k; ++j) {
+        double sacc = 0.0;
+        if (i < k && i >= j) {
+            sacc = C[(size_t)i * k + j];
+            for (int q = 0; q < j; ++q) sacc -= L[i * ld + q] * L[j * ld + q];
+            if (i == j) {
+                if (!(sacc > floor_)) sacc = floor_;
+                L[j * ld + j] = sqrt(sacc);
+            }
+        }
+        __syncthreads();
+        if (i < k && i > j) L[i * ld + j] = sacc / L[j * ld + j];
+        __syncthreads();
+    }
+    for (int idx = i; idx < k * k; idx += 128) {
+        const int r = idx / k, q = idx % k;
+        Lout[idx] = (q <= r) ? L[r * ld + q] : 0.0;
+    }
+}
+
+// Q = L^-1 R for R[k,d] (rows), one thread per column of R: forward substitution with the column in registers.
+template <int KMAX>
+__global__ void __launch_bounds__(128)
+trsm_rows_kernel(const double *__restrict__ Lg, int k, const double *__restrict__ R, int d, double *__restrict__ Q) {
+    extern __shared__ double smd[];
+    double *L = smd;                    // [k][k]
+    for (int idx = threadIdx.x; idx < k * k; idx += 128) L[idx] = Lg[idx];
+    __syncthreads();
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col >= d) return;
+    double q[KMAX];
+#pragma unroll
+    for (int r = 0; r < KMAX; ++r) {
+        if (r < k) {
+            double sacc = R[(size_t)r * d + col];
+#pragma unroll
+            for (int p = 0; p < KMAX; ++p)
+                if (p < r) sacc -= L[r * k + p] * q[p];
+            q[r] = sacc / L[r * k + r];
+            Q[(size_t)r * d + col] = q[r];
+        }
+    }
+}
+
+__global__ void symmetrize_kernel(double *__restrict__ H, int n) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int i = idx / n, j = idx % n;
+    if (j > i) {
+        const double v = 0.5 * (H[(size_t)i * n + j] + H[(size_t)j * n + i]);
+        H[(size_t)i * n + j] = v;
+        H[(size_t)j * n + i] = v;
+    }
+}
+
+// svd_flip sign rule on the rows of V[c,d] (largest |.| entry positive; first index on ties)
+__global__ void sign_rows_kernel(double *__restrict__ V, int c, int d) {
+    const int lane = threadIdx.x & 31, t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= c) return;
+    double *row = V + (size_t)t * d;
+    double best = -1.0, bval = 0.0;
+    int bi = 0;
+    for (int i = lane; i < d; i += 32) {
+        const double az = fabs(row[i]);
+        if (az > best) { best = az; bi = i; bval = row[i]; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o), ov = __shfl_xor_sync(0xffffffffu, bval, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; bval = ov; }
+    }
+    if (bval < 0.0)
+        for (int i = lane; i < d; i += 32) row[i] = -row[i];
+}
+
+struct LanczosWs {
+    double *QbT, *RT, *T, *C, *Linv, *WT, *H, *U, *lamH;
+    void *eig_ws;
+    size_t bytes;
+};
+static LanczosWs carve_lanczos(void *base, int d, int c) {
+    LanczosWs w;
+    char *p = reinterpret_cast<char *>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char *q = p + off; off += align_up(bytes, 256); return q; };
+    const int kd = 3 * c;
+    w.QbT = (double *)take((size_t)kd * d * 8);
+    w.RT = (double *)take((size_t)c * d * 8);
+    w.T = (double *)take((size_t)c * kd * 8);
+    w.C = (double *)take((size_t)c * c * 8);
+    w.Linv = (double *)take((size_t)c * c * 8);
+    w.WT = (double *)take((size_t)kd * d * 8);
+    w.H = (double *)take((size_t)kd * kd * 8);
+    w.U = (double *)take((size_t)c * kd * 8);
+    w.lamH = (double *)take((size_t)c * 8);
+    w.eig_ws = take(carve(nullptr, kd, c).bytes);
+    w.bytes = off;
+    return w;
+}
+static bool lanczos_applicable(int d, int c) {
+    static int enabled = -1;
+    if (enabled == -1) {
+        const char *env = getenv("GANSPACE_B200_CHAIN");
+        enabled = (env && strcmp(env, "direct") == 0) ? 0 : 1;
+    }
+    return enabled && c % 16 == 0 && c <= 128 && 3 * c <= d / 2 + d / 8 && 3 * c <= 512;
+}
+
+// orthonormalise the rows of RT[k,d] (CholQR, twice) into out[k,d]; RT is used as scratch
+static int cholqr2_rows(const LanczosWs &lw, double *RT, double *out, int k, int d, cudaStream_t st) {
+    const size_t smem_c = (size_t)k * (k + 1) * sizeof(double), smem_t = (size_t)k * k * sizeof(double);
+    static size_t set_c = 0, set_t = 0;
+    if (smem_c > set_c) {
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        set_c = smem_c;
+    }
+    if (smem_t > set_t) {
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(trsm_rows_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(trsm_rows_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(trsm_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        set_t = smem_t;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        const double *src = (pass == 0) ? RT : out;
+        double *dst = (pass == 0) ? out : RT;
+        if (int r = dgemm<false, true>(k, k, d, 1.0, src, d, src, d, 0.0, lw.C, k, st)) return r;       // C = R R^T
+        chol_kernel<<<1, 128, smem_c, st>>>(lw.C, k, lw.Linv);                                         // Linv holds L
+        GSB_CHECK_LAUNCH();
+        const unsigned grid = (unsigned)((d + 127) / 128);
+        if (k <= 32) trsm_rows_kernel<32><<<grid, 128, smem_t, st>>>(lw.Linv, k, src, d, dst);
+        else if (k <= 80) trsm_rows_kernel<80><<<grid, 128, smem_t, st>>>(lw.Linv, k, src, d, dst);
+        else trsm_rows_kernel<128><<<grid, 128, smem_t, st>>>(lw.Linv, k, src, d, dst);
+        GSB_CHECK_LAUNCH();
+    }
+    GSB_CHECK_CUDA(cudaMemcpyAsync(out, RT, (size_t)k * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return GSB_OK;
+}
+
+// top-c eigenpairs of the symmetric G[d,d] from the block Krylov space of the previous components Vprev[c,d]
+static int eig_top_lanczos(const LanczosWs &lw, const double *G, const double *Vprev, int d, int c, double *evals,
+                           double *evecs, cudaStream_t st) {
+    const int kd = 3 * c;
+    GSB_CHECK_CUDA(cudaMemcpyAsync(lw.QbT, Vprev, (size_t)c * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    for (int j = 0; j < 2; ++j) {
+        const int kb = (j + 1) * c;                       // rows of the basis built so far
+        const double *Qj = lw.QbT + (size_t)j * c * d;
+        double *Wj = lw.WT + (size_t)j * c * d;                                                           // rows j of W = Qb G
+        if (int r = dgemm<false, false>(c, d, d, 1.0, Qj, d, G, d, 0.0, Wj, d, st)) return r;             // W_j = Q_j G
+        GSB_CHECK_CUDA(cudaMemcpyAsync(lw.RT, Wj, (size_t)c * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        for (int pass = 0; pass < 2; ++pass) {                                                           // R -= (R B^T) B
+            if (int r = dgemm<false, true>(c, kb, d, 1.0, lw.RT, d, lw.QbT, d, 0.0, lw.T, kb, st)) return r;
+            if (int r = dgemm<false, false>(c, d, kb, -1.0, lw.T, kb, lw.QbT, d, 1.0, lw.RT, d, st)) return r;
+        }
+        if (int r = cholqr2_rows(lw, lw.RT, lw.QbT + (size_t)kb * d, c, d, st)) return r;
+    }
+    if (int r = dgemm<false, false>(c, d, d, 1.0, lw.QbT + (size_t)2 * c * d, d, G, d, 0.0, lw.WT + (size_t)2 * c * d, d,
+                                    st)) return r;                                                        // W_2 = Q_2 G
+    if (int r = dgemm<false, true>(kd, kd, d, 1.0, lw.WT, d, lw.QbT, d, 0.0, lw.H, kd, st)) return r;      // H = W Qb^T
+    symmetrize_kernel<<<(kd * kd + 255) / 256, 256, 0, st>>>(lw.H, kd);
+    GSB_CHECK_LAUNCH();
+    Workspace ew = carve(lw.eig_ws, kd, c);
+    GSB_CHECK_CUDA(cudaMemcpyAsync(ew.A, lw.H, (size_t)kd * kd * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (int r = eig_top(ew, kd, c, evals, lw.U, st)) return r;
+    if (int r = dgemm<false, false>(c, d, kd, 1.0, lw.U, kd, lw.QbT, d, 0.0, evecs, d, st)) return r;      // V = U Qb
+    sign_rows_kernel<<<(c + 7) / 8, 256, 0, st>>>(evecs, c, d);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
 static int check_dims(int d, int c) {
     GSB_CHECK_ARG(d >= 32 && d <= 1024 && d % 32 == 0, "ipca: small-d engine needs 32 <= d <= 1024, d%%32==0 (d=%d)", d);
     GSB_CHECK_ARG(c >= 1 && c <= d, "ipca: need 1 <= c <= d (c=%d d=%d)", c, d);
@@ -892,7 +1146,9 @@ extern "C" size_t gsb_ipca_state_bytes(int d, int c) {
 }
 
 extern "C" size_t gsb_ipca_workspace_bytes(int d, int c) {
-    return gsb::carve(nullptr, d, c).bytes;
+    size_t b = gsb::carve(nullptr, d, c).bytes;
+    if (gsb::lanczos_applicable(d, c)) b += gsb::carve_lanczos(nullptr, d, c).bytes;
+    return b;
 }
 
 extern "C" int gsb_ipca_reset(void *d_state, int d, int c, gsb_stream_t stream) {
@@ -922,7 +1178,16 @@ extern "C" int gsb_ipca_chain_step(void *d_state, int d, int c, int64_t n_seen, 
     gsb::build_g_kernel<<<grid, block, 0, st>>>(d_gram_b, d_mean_b, s.mean, s.S, s.V, d, c, (double)n_seen,
                                                 (double)n_batch, w.A);
     GSB_CHECK_LAUNCH();
-    if (int r = gsb::eig_top(w, d, c, w.lam, w.evecs, st)) return r;
+    if (n_seen > 0 && gsb::lanczos_applicable(d, c)) {
+        gsb::LanczosWs lw = gsb::carve_lanczos(reinterpret_cast<char *>(d_workspace) + w.bytes, d, c);
+        if (workspace_bytes < w.bytes + lw.bytes) {
+            gsb::set_error("ipca_chain_step: workspace too small (%zu < %zu)", workspace_bytes, w.bytes + lw.bytes);
+            return GSB_ERR_WORKSPACE;
+        }
+        if (int r = gsb::eig_top_lanczos(lw, w.A, s.V, d, c, w.lam, w.evecs, st)) return r;
+    } else {
+        if (int r = gsb::eig_top(w, d, c, w.lam, w.evecs, st)) return r;
+    }
     size_t tot = (size_t)c * d;
     gsb::finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
         s.hdr, s.mean, s.unnorm, s.S, s.V, d_mean_b, d_gram_b, w.lam, w.evecs, d, c, (double)n_seen,

@@ -10,8 +10,8 @@
 // one CTA per stream, all streams of a run in one launch (101 CTAs on 148 SMs for config 2):
 //   1. the CTA regenerates 16 x 624 state words (3 barrier-separated phases per 624, ping-pong in smem),
 //      tempering them into a 9984-word smem buffer;
-//   2. 256 threads turn those words into 2496 polar-method attempts (fp64, no FMA contraction so the
-//      accept/reject decisions are those of the C code NumPy runs), thread t owning 10 consecutive
+//   2. 1024 threads turn those words into 2496 polar-method attempts (fp64, no FMA contraction so the
+//      accept/reject decisions are those of the C code NumPy runs), thread t owning 3 consecutive
 //      attempts so that output order == thread order;
 //   3. a block scan of the accept counts gives each thread its output offset (order-preserving
 //      compaction of the rejection sampler); log/div/sqrt run only for accepted pairs, whose results
@@ -23,11 +23,11 @@ namespace gsb {
 
 constexpr int MT_N = 624;
 constexpr int MT_M = 397;
-constexpr int RNG_THREADS = 256;
+constexpr int RNG_THREADS = 1024;   // 32 warps: the fp64 log/div/sqrt chains of the transform need the TLP
 constexpr int BLOCKS_PER_SUPER = 16;
 constexpr int WORDS_PER_SUPER = MT_N * BLOCKS_PER_SUPER;   // 9984
 constexpr int ATT_PER_SUPER = WORDS_PER_SUPER / 4;         // 2496 polar attempts
-constexpr int ATT_PER_THREAD = 10;                         // 256*10 >= 2496
+constexpr int ATT_PER_THREAD = 3;                          // 1024*3 >= 2496
 
 enum { MODE_RAW = 0, MODE_NORMAL = 1, MODE_TRUNCNORM = 2 };
 
@@ -133,7 +133,7 @@ mt_stream_kernel(const uint32_t *__restrict__ seeds, int64_t n_per_stream, void 
             continue;
         }
 
-        // ---- 2. accept/reject this thread's 10 consecutive attempts (cheap part only) -------------
+        // ---- 2. accept/reject this thread's consecutive attempts (cheap part only) -------------
         unsigned accept = 0;
 #pragma unroll
         for (int j = 0; j < ATT_PER_THREAD; ++j) {
