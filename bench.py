@@ -224,7 +224,7 @@ def run_ours(args):
             "e2e": {"value": N / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 4 * (pl.n_calls + 1), "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "mapping MLP (pixelnorm + 8 x sgemm_tn_bias_act_kernel)",
+            "roofline": {"bound": "tensor", "kernel": "mapping MLP: pixelnorm_split + 8 x mapping_layer_tc_kernel (tcgen05, fp16 hi/lo x3)" if os.environ.get("GANSPACE_B200_MAPPING", "tc") != "simt" else "mapping MLP: pixelnorm + 8 x sgemm_tn_bias_act_kernel (fp32 FMA)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
                          "peak_source": f"bf16_tflops_sustained, {peak_kind} (MEASURED_PEAKS.json)",

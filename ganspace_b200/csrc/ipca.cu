@@ -953,22 +953,31 @@ static int dgemm(int M, int N, int K, double alpha, const double *A, int lda, co
     return GSB_OK;
 }
 
-// Left-looking Cholesky of the k x k Gram matrix C (k <= 128), one CTA of 128 threads (thread i owns row i):
-// L[i][j] = (C[i][j] - sum_{q<j} L[i][q] L[j][q]) / L[j][j].  Pivots below 1e-26 * max diagonal are clamped
-// (numerically dependent residual directions).  Writes L (row-major, zero upper part).
+// Left-looking Cholesky of the k x k Gram matrix C (k <= 128), one CTA of 128 threads.  Thread i owns row i of L:
+// L[i][j] = (C[i][j] - sum_{q<j} L[i][q] L[j][q]) / L[j][j].  The dot products run on four independent
+// accumulators (they are latency-bound dependent DFMA chains otherwise).  Pivots below 1e-26 * max diagonal are
+// clamped (numerically dependent residual directions).
 __global__ void __launch_bounds__(128)
 chol_kernel(const double *__restrict__ C, int k, double *__restrict__ Lout) {
     extern __shared__ double smd[];
-    double *L = smd;                    // [k][k+1]
+    double *L = smd;                         // [k][k+1]
     const int i = threadIdx.x, ld = k + 1;
+    for (int idx = i; idx < k * k; idx += 128) L[(idx / k) * ld + idx % k] = C[idx];   // stage C: no global loads in the chain
+    __syncthreads();
     double dmax = 0.0;
-    for (int j = 0; j < k; ++j) dmax = fmax(dmax, C[(size_t)j * k + j]);
+    for (int j = 0; j < k; ++j) dmax = fmax(dmax, L[j * ld + j]);
     const double floor_ = fmax(dmax * 1e-26, 1e-300);
     for (int j = 0; j < k; ++j) {
         double sacc = 0.0;
         if (i < k && i >= j) {
-            sacc = C[(size_t)i * k + j];
-            for (int q = 0; q < j; ++q) sacc -= L[i * ld + q] * L[j * ld + q];
+            double a0 = L[i * ld + j], a1 = 0.0, a2 = 0.0, a3 = 0.0;     // lower triangle still holds C
+            const double *li = L + i * ld, *lj = L + j * ld;
+            int q = 0;
+            for (; q + 4 <= j; q += 4) {
+                a0 -= li[q] * lj[q]; a1 -= li[q + 1] * lj[q + 1]; a2 -= li[q + 2] * lj[q + 2]; a3 -= li[q + 3] * lj[q + 3];
+            }
+            for (; q < j; ++q) a0 -= li[q] * lj[q];
+            sacc = (a0 + a1) + (a2 + a3);
             if (i == j) {
                 if (!(sacc > floor_)) sacc = floor_;
                 L[j * ld + j] = sqrt(sacc);
@@ -984,7 +993,8 @@ chol_kernel(const double *__restrict__ C, int k, double *__restrict__ Lout) {
     }
 }
 
-// Q = L^-1 R for R[k,d] (rows), one thread per column of R: forward substitution with the column in registers.
+// Q = L^-1 R for R[k,d] (rows): one thread per column of R, forward substitution with the solved column kept in
+// registers and the row dot products on four independent accumulators.
 template <int KMAX>
 __global__ void __launch_bounds__(128)
 trsm_rows_kernel(const double *__restrict__ Lg, int k, const double *__restrict__ R, int d, double *__restrict__ Q) {
@@ -996,16 +1006,28 @@ trsm_rows_kernel(const double *__restrict__ Lg, int k, const double *__restrict_
     if (col >= d) return;
     double q[KMAX];
 #pragma unroll
+    for (int r = 0; r < KMAX; ++r) q[r] = (r < k) ? R[(size_t)r * d + col] : 0.0;     // all loads in flight at once
+#pragma unroll
     for (int r = 0; r < KMAX; ++r) {
         if (r < k) {
-            double sacc = R[(size_t)r * d + col];
+            double a0 = q[r], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double *lr = L + r * k;
 #pragma unroll
-            for (int p = 0; p < KMAX; ++p)
-                if (p < r) sacc -= L[r * k + p] * q[p];
-            q[r] = sacc / L[r * k + r];
-            Q[(size_t)r * d + col] = q[r];
+            for (int p = 0; p + 3 < KMAX; p += 4) {
+                if (p + 3 < r) {
+                    a0 -= lr[p] * q[p]; a1 -= lr[p + 1] * q[p + 1]; a2 -= lr[p + 2] * q[p + 2]; a3 -= lr[p + 3] * q[p + 3];
+                } else {
+                    if (p < r) a0 -= lr[p] * q[p];
+                    if (p + 1 < r) a1 -= lr[p + 1] * q[p + 1];
+                    if (p + 2 < r) a2 -= lr[p + 2] * q[p + 2];
+                }
+            }
+            q[r] = ((a0 + a1) + (a2 + a3)) / lr[r];
         }
     }
+#pragma unroll
+    for (int r = 0; r < KMAX; ++r)
+        if (r < k) Q[(size_t)r * d + col] = q[r];
 }
 
 __global__ void symmetrize_kernel(double *__restrict__ H, int n) {
