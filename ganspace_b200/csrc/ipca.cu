@@ -993,41 +993,43 @@ chol_kernel(const double *__restrict__ C, int k, double *__restrict__ Lout) {
     }
 }
 
-// Q = L^-1 R for R[k,d] (rows): one thread per column of R, forward substitution with the solved column kept in
-// registers and the row dot products on four independent accumulators.
-template <int KMAX>
-__global__ void __launch_bounds__(128)
+// Q = L^-1 R for R[k,d] (rows): one thread per column of R; the solved column lives in shared memory
+// ([k][64], conflict-free) so that the loops stay rolled (a fully unrolled register version thrashes the
+// instruction cache); row dot products on four independent accumulators.
+constexpr int TRSM_THREADS = 64;
+__global__ void __launch_bounds__(TRSM_THREADS)
 trsm_rows_kernel(const double *__restrict__ Lg, int k, const double *__restrict__ R, int d, double *__restrict__ Q) {
     extern __shared__ double smd[];
-    double *L = smd;                    // [k][k]
-    for (int idx = threadIdx.x; idx < k * k; idx += 128) L[idx] = Lg[idx];
+    double *L = smd;                              // [k][k]
+    double *qs = smd + (size_t)k * k;             // [k][TRSM_THREADS]
+    for (int idx = threadIdx.x; idx < k * k; idx += TRSM_THREADS) L[idx] = Lg[idx];
+    const int col = blockIdx.x * TRSM_THREADS + threadIdx.x;
+    const bool ok = col < d;
+    double *q = qs + threadIdx.x;
+    for (int r = 0; r < k; ++r) q[r * TRSM_THREADS] = ok ? R[(size_t)r * d + col] : 0.0;
     __syncthreads();
-    const int col = blockIdx.x * 128 + threadIdx.x;
-    if (col >= d) return;
-    double q[KMAX];
-#pragma unroll
-    for (int r = 0; r < KMAX; ++r) q[r] = (r < k) ? R[(size_t)r * d + col] : 0.0;     // all loads in flight at once
-#pragma unroll
-    for (int r = 0; r < KMAX; ++r) {
-        if (r < k) {
-            double a0 = q[r], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            const double *lr = L + r * k;
-#pragma unroll
-            for (int p = 0; p + 3 < KMAX; p += 4) {
-                if (p + 3 < r) {
-                    a0 -= lr[p] * q[p]; a1 -= lr[p + 1] * q[p + 1]; a2 -= lr[p + 2] * q[p + 2]; a3 -= lr[p + 3] * q[p + 3];
-                } else {
-                    if (p < r) a0 -= lr[p] * q[p];
-                    if (p + 1 < r) a1 -= lr[p + 1] * q[p + 1];
-                    if (p + 2 < r) a2 -= lr[p + 2] * q[p + 2];
-                }
-            }
-            q[r] = ((a0 + a1) + (a2 + a3)) / lr[r];
+    for (int r = 0; r < k; ++r) {
+        const double *lr = L + r * k;
+        double a0 = q[r * TRSM_THREADS], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int p = 0;
+        for (; p + 4 <= r; p += 4) {
+            a0 -= lr[p] * q[p * TRSM_THREADS];
+            a1 -= lr[p + 1] * q[(p + 1) * TRSM_THREADS];
+            a2 -= lr[p + 2] * q[(p + 2) * TRSM_THREADS];
+            a3 -= lr[p + 3] * q[(p + 3) * TRSM_THREADS];
         }
+        for (; p < r; ++p) a0 -= lr[p] * q[p * TRSM_THREADS];
+        q[r * TRSM_THREADS] = ((a0 + a1) + (a2 + a3)) / lr[r];
     }
-#pragma unroll
-    for (int r = 0; r < KMAX; ++r)
-        if (r < k) Q[(size_t)r * d + col] = q[r];
+    if (ok)
+        for (int r = 0; r < k; ++r) Q[(size_t)r * d + col] = q[r * TRSM_THREADS];
+}
+
+// Newton-Schulz polish of an almost orthonormal row block: given C = Q Q^T, writes N = 1.5 I - 0.5 C so that
+// Q <- N Q has orthogonality error O(||C - I||^2).
+__global__ void ns_matrix_kernel(const double *__restrict__ C, int k, double *__restrict__ N) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < k * k) N[idx] = ((idx / k == idx % k) ? 1.5 : 0.0) - 0.5 * C[idx];
 }
 
 __global__ void symmetrize_kernel(double *__restrict__ H, int n) {
@@ -1094,33 +1096,34 @@ static bool lanczos_applicable(int d, int c) {
     return enabled && c % 16 == 0 && c <= 128 && 3 * c <= d / 2 + d / 8 && 3 * c <= 512;
 }
 
-// orthonormalise the rows of RT[k,d] (CholQR, twice) into out[k,d]; RT is used as scratch
+// orthonormalise the rows of RT[k,d] into out[k,d]: one CholQR pass (Gram, Cholesky, triangular solve) followed
+// by two Newton-Schulz polishing steps (Gram + small GEMM each; quadratic, no sequential dependency).  RT is scratch.
 static int cholqr2_rows(const LanczosWs &lw, double *RT, double *out, int k, int d, cudaStream_t st) {
-    const size_t smem_c = (size_t)k * (k + 1) * sizeof(double), smem_t = (size_t)k * k * sizeof(double);
+    const size_t smem_c = (size_t)k * (k + 1) * sizeof(double);
+    const size_t smem_t = ((size_t)k * k + (size_t)k * TRSM_THREADS) * sizeof(double);
     static size_t set_c = 0, set_t = 0;
     if (smem_c > set_c) {
         GSB_CHECK_CUDA(cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         set_c = smem_c;
     }
     if (smem_t > set_t) {
-        GSB_CHECK_CUDA(cudaFuncSetAttribute(trsm_rows_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-        GSB_CHECK_CUDA(cudaFuncSetAttribute(trsm_rows_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-        GSB_CHECK_CUDA(cudaFuncSetAttribute(trsm_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
         set_t = smem_t;
     }
+    if (int r = dgemm<false, true>(k, k, d, 1.0, RT, d, RT, d, 0.0, lw.C, k, st)) return r;             // C = R R^T
+    chol_kernel<<<1, 128, smem_c, st>>>(lw.C, k, lw.Linv);                                             // Linv holds L
+    GSB_CHECK_LAUNCH();
+    trsm_rows_kernel<<<(unsigned)((d + TRSM_THREADS - 1) / TRSM_THREADS), TRSM_THREADS, smem_t, st>>>(lw.Linv, k, RT, d, out);
+    GSB_CHECK_LAUNCH();
+    double *cur = out, *nxt = RT;
     for (int pass = 0; pass < 2; ++pass) {
-        const double *src = (pass == 0) ? RT : out;
-        double *dst = (pass == 0) ? out : RT;
-        if (int r = dgemm<false, true>(k, k, d, 1.0, src, d, src, d, 0.0, lw.C, k, st)) return r;       // C = R R^T
-        chol_kernel<<<1, 128, smem_c, st>>>(lw.C, k, lw.Linv);                                         // Linv holds L
+        if (int r = dgemm<false, true>(k, k, d, 1.0, cur, d, cur, d, 0.0, lw.C, k, st)) return r;       // C = Q Q^T
+        ns_matrix_kernel<<<(k * k + 255) / 256, 256, 0, st>>>(lw.C, k, lw.Linv);
         GSB_CHECK_LAUNCH();
-        const unsigned grid = (unsigned)((d + 127) / 128);
-        if (k <= 32) trsm_rows_kernel<32><<<grid, 128, smem_t, st>>>(lw.Linv, k, src, d, dst);
-        else if (k <= 80) trsm_rows_kernel<80><<<grid, 128, smem_t, st>>>(lw.Linv, k, src, d, dst);
-        else trsm_rows_kernel<128><<<grid, 128, smem_t, st>>>(lw.Linv, k, src, d, dst);
-        GSB_CHECK_LAUNCH();
+        if (int r = dgemm<false, false>(k, d, k, 1.0, lw.Linv, k, cur, d, 0.0, nxt, d, st)) return r;   // Q <- N Q
+        double *t = cur; cur = nxt; nxt = t;
     }
-    GSB_CHECK_CUDA(cudaMemcpyAsync(out, RT, (size_t)k * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (cur != out) GSB_CHECK_CUDA(cudaMemcpyAsync(out, cur, (size_t)k * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
     return GSB_OK;
 }
 
