@@ -243,7 +243,7 @@ class PackedMapping:
                               "results are invalid (set GANSPACE_B200_MAPPING=simt)")
 
     def forward(self, z: torch.Tensor, out: torch.Tensor = None, pixelnorm: bool = True,
-                force_simt: bool = None) -> torch.Tensor:
+                force_simt: bool = None, leave_free_sms: int = 0) -> torch.Tensor:
         lib = load()
         if force_simt is None:
             force_simt = os.environ.get("GANSPACE_B200_MAPPING", MAPPING_DEFAULT) == "simt"
@@ -256,7 +256,7 @@ class PackedMapping:
             out = torch.empty_like(z2)
         ws_bytes = lib.gsb_mapping_workspace_bytes(n, self.dim)
         ws = scratch.get("mapping", ws_bytes, z.device)
-        flags = (1 if pixelnorm else 0) | (2 if force_simt else 0)
+        flags = (1 if pixelnorm else 0) | (2 if force_simt else 0) | ((int(leave_free_sms) & 0xff) << 8)
         with torch.cuda.device(z.device), instrument.section("mapping"):
             _check(lib.gsb_mapping_forward(_ptr(self.packed), self.n_layers, self.dim, _ptr(z2), _ptr(out), n,
                                            flags, _ptr(ws), ws.numel(), _stream()), "gsb_mapping_forward")
@@ -352,7 +352,9 @@ class IPCAChain:
                 _check(lib.gsb_ipca_chain_step(_ptr(self.state), self.d, self.c, self.n_seen, int(n_batch),
                                                _ptr(mean_b), _ptr(gram_b), _ptr(self.ws), self.ws.numel(), _stream()),
                        "gsb_ipca_chain_step")
-        instrument.count(8)
+        # kernels per step: direct path 8; block-Lanczos path 38 (15 dgemm, chol, trsm, 4 Newton-Schulz, eigensolver, ...)
+        lanczos = self.n_seen > 0 and self.c % 16 == 0 and self.c <= 128 and 3 * self.c <= self.d // 2 + self.d // 8
+        instrument.count(38 if lanczos else 8)
         self.n_seen += int(n_batch)
 
     def join(self):

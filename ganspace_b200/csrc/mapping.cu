@@ -18,7 +18,7 @@ namespace gsb {
 size_t mapping_tc_packed_bytes(int n_layers, int dim);
 int mapping_tc_pack(const float *pw, int n_layers, int dim, void *tc_base, cudaStream_t st);
 int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim, const float *d_z, float *d_w,
-                       int64_t n, bool pixelnorm, void *ws, cudaStream_t st);
+                       int64_t n, bool pixelnorm, void *ws, int leave_free_sms, cudaStream_t st);
 size_t mapping_tc_workspace_bytes(int64_t n, int dim);
 unsigned *mapping_tc_overflow_flag(void *tc_base, int n_layers, int dim);
 
@@ -225,7 +225,7 @@ extern "C" int gsb_mapping_forward(const void *d_packed, int n_layers, int dim, 
     if (!(flags & 2) && gsb::tc_supported(n_layers, dim)) {
         void *tc_base = reinterpret_cast<char *>(const_cast<void *>(d_packed)) + gsb::simt_packed_bytes(n_layers, dim);
         return gsb::mapping_forward_tc(pb, tc_base, n_layers, dim, d_z, d_w, n, (flags & 1) != 0, d_workspace,
-                                       (cudaStream_t)stream);
+                                       (flags >> 8) & 0xff, (cudaStream_t)stream);
     }
     float *tmp0 = reinterpret_cast<float *>(d_workspace);
     float *tmp1 = reinterpret_cast<float *>(reinterpret_cast<char *>(d_workspace) +

@@ -431,7 +431,8 @@ int mapping_tc_pack(const float *pw, int n_layers, int dim, void *tc_base, cudaS
 
 // Full mapping network on the tensor cores.  ws: 4 fp16 buffers of n*dim (two hi/lo ping-pong pairs).
 int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim,
-                       const float *d_z, float *d_w, int64_t n, bool pixelnorm, void *ws, cudaStream_t st) {
+                       const float *d_z, float *d_w, int64_t n, bool pixelnorm, void *ws, int leave_free_sms,
+                       cudaStream_t st) {
     GSB_CHECK_ARG(dim % TC_BLOCK_N == 0 && dim % TC_BLOCK_K == 0, "mapping_forward_tc: dim must be a multiple of 256");
     GSB_CHECK_ARG(n < (1ll << 31), "mapping_forward_tc: too many rows");
     TcPackView v = tc_pack_view(tc_base, n_layers, dim);
@@ -449,7 +450,11 @@ int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim,
                                                                   v.overflow);
     GSB_CHECK_LAUNCH();
     const int num_tiles = (int)((n + TC_BLOCK_M - 1) / TC_BLOCK_M) * (dim / TC_BLOCK_N);
-    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    // persistent CTAs, one per SM; `leave_free_sms` keeps some SMs idle for a concurrent latency-critical stream
+    // (the IPCA chain's 16-CTA cluster kernels), which otherwise wait for a whole layer launch to drain
+    int avail = num_sms() - leave_free_sms;
+    if (avail < 16) avail = 16;
+    const int grid = num_tiles < avail ? num_tiles : avail;
     const int64_t per = (int64_t)dim * dim;
     for (int l = 0; l < n_layers; ++l) {
         const int src = l & 1, dst = src ^ 1;

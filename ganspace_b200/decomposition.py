@@ -98,6 +98,18 @@ def _sample_batches(model, Bsz, seeds, out=None):
     return torch.cat([model.sample_latent(Bsz, seed=s) for s in seeds], dim=0)
 
 
+def _sample_batches_lazy(model, Bsz, seeds):
+    """Like _sample_batches, plus ``ensure(row_end)``: rows [0, row_end) are final once it returns.  Models whose
+    sample_latent has a second stage (StyleGAN2 W space: the mapping network) run it chunk by chunk on demand,
+    so the IPCA chain starts on the first groups while later rows are still being mapped."""
+    if hasattr(model, "sample_latents_multi"):
+        try:
+            return model.sample_latents_multi(Bsz, seeds, lazy=True)
+        except TypeError:
+            pass
+    return _sample_batches(model, Bsz, seeds), (lambda row_end: None)
+
+
 # Solve for directions in latent space that match PCs in activation space (reference :77-139)
 def linreg_lstsq(comp_np, mean_np, stdev_np, inst, config, affine=None):
     """``affine``: when the hooked layer is affine in the latent (models/biggan.py AffineLayer), comp/mean are
@@ -234,11 +246,12 @@ def compute_arrays(config, instrumented_model):
         runs = _plan.contiguous_runs(mine)
         # every sample_latent call this rank needs for the chunk, generated by ONE launch (one CTA per seed)
         needed, offsets = _plan.batch_slots(pl, runs)
-        lat = _sample_batches(model, B, [seeds[b] for b in needed])
+        lat, ensure_rows = _sample_batches_lazy(model, B, [seeds[b] for b in needed])
         lat = lat.reshape(lat.shape[0], -1)
         for run, off in zip(runs, offsets):
             for k in run:
                 r = off + (k - run[0]) * NB
+                ensure_rows(r + NB)
                 rows = lat[r:r + NB]
                 if samples_are_latents:
                     X = rows
@@ -260,6 +273,7 @@ def compute_arrays(config, instrumented_model):
                         slots[k, d * d:] = mean_b
                 elif not transformer.fit_partial(X):
                     break
+        ensure_rows(lat.shape[0])
         del lat    # X (a view of the last group when samples_are_latents) keeps its storage alive
     if live:
         import torch.distributed as dist

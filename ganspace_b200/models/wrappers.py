@@ -151,17 +151,32 @@ class StyleGAN2(BaseModel):
             z = self.model.style(z)
         return z
 
-    def sample_latents_multi(self, n_samples, seeds, out=None):
+    def sample_latents_multi(self, n_samples, seeds, out=None, lazy=False):
         """Several ``sample_latent(n_samples, seed=s)`` calls in ONE launch (one CTA per seed);
         ``out`` is an optional [len(seeds)*n_samples, 512] device buffer.  Used by the decomposition
-        driver so that a whole run's ~100 independent streams fill the machine."""
+        driver so that a whole run's ~100 independent streams fill the machine.
+        ``lazy=True`` (W space): returns (z, ensure) where ``ensure(row_end)`` maps rows [0, row_end) to W in
+        place, chunk by chunk, so that the consumer of the first rows does not wait for the last ones."""
         S = len(seeds)
         z = _native.legacy_normal(list(seeds), 512 * n_samples, self.device,
                                   out=None if out is None else out.view(S, 512 * n_samples))
         z = z.view(S * n_samples, 512)
-        if self.w_primary:
-            z = self.model.style(z) if out is None else self.model.style.packed().forward(z, out=z)
-        return z
+        if not self.w_primary:
+            return (z, lambda row_end: None) if lazy else z
+        if lazy:
+            packed = self.model.style.packed()
+            state = {"hi": 0}
+            total = z.shape[0]
+
+            def ensure(row_end, chunk=max(4 * n_samples, 40_000)):
+                while state["hi"] < min(row_end, total):
+                    a = state["hi"]
+                    b = min(total, a + chunk)
+                    # later chunks run next to the IPCA chain: leave it a GPC's worth of SMs
+                    packed.forward(z[a:b], out=z[a:b], leave_free_sms=0 if a == 0 else 20)
+                    state["hi"] = b
+            return z, ensure
+        return self.model.style(z) if out is None else self.model.style.packed().forward(z, out=z)
 
     def check_numerics(self):
         """Raise if a kernel flagged an out-of-range activation since the weights were packed (synchronises)."""

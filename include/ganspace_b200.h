@@ -75,7 +75,8 @@ size_t gsb_mapping_workspace_bytes(int64_t n, int dim);
 /* flags: bit0 = apply PixelNorm first (always set for Generator.style); bit1 = force the SIMT fp32
  * kernels (reference-grade fp32 FMA path used to validate the tensor-core path); default = tcgen05 path
  * (fp16 hi/lo operand split, 3 MMAs per product, fp32 accumulation in TMEM) when dim % 256 == 0.
- * n_layers == 0 with bit0 set runs PixelNorm alone (d_packed may be NULL). */
+ * n_layers == 0 with bit0 set runs PixelNorm alone (d_packed may be NULL).  bits 8-15 = number of SMs the
+ * persistent tensor-core kernel leaves idle for a concurrent latency-critical stream (0 = use all). */
 int gsb_mapping_forward(const void *d_packed, int n_layers, int dim, const float *d_z, float *d_w,
                         int64_t n, int flags, void *d_workspace, size_t workspace_bytes,
                         gsb_stream_t stream);
