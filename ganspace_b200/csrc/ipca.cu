@@ -953,41 +953,39 @@ static int dgemm(int M, int N, int K, double alpha, const double *A, int lda, co
     return GSB_OK;
 }
 
-// Left-looking Cholesky of the k x k Gram matrix C (k <= 128), one CTA of 128 threads.  Thread i owns row i of L:
-// L[i][j] = (C[i][j] - sum_{q<j} L[i][q] L[j][q]) / L[j][j].  The dot products run on four independent
-// accumulators (they are latency-bound dependent DFMA chains otherwise).  Pivots below 1e-26 * max diagonal are
-// clamped (numerically dependent residual directions).
-__global__ void __launch_bounds__(128)
+// Right-looking Cholesky of the k x k Gram matrix C (k <= 128) in shared memory, one CTA of 256 threads
+// (8 warps): per column j a pivot, a column scale and a rank-1 update of the trailing lower triangle spread
+// over all threads (lane <-> column q, warp <-> row i), three barriers per column.  Pivots below
+// 1e-26 * max diagonal are clamped (numerically dependent residual directions).  Writes L (zero upper part).
+__global__ void __launch_bounds__(256)
 chol_kernel(const double *__restrict__ C, int k, double *__restrict__ Lout) {
     extern __shared__ double smd[];
     double *L = smd;                         // [k][k+1]
-    const int i = threadIdx.x, ld = k + 1;
-    for (int idx = i; idx < k * k; idx += 128) L[(idx / k) * ld + idx % k] = C[idx];   // stage C: no global loads in the chain
+    __shared__ double s_floor;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, ld = k + 1;
+    for (int idx = tid; idx < k * k; idx += 256) L[(idx / k) * ld + idx % k] = C[idx];
     __syncthreads();
-    double dmax = 0.0;
-    for (int j = 0; j < k; ++j) dmax = fmax(dmax, L[j * ld + j]);
-    const double floor_ = fmax(dmax * 1e-26, 1e-300);
+    if (tid == 0) {
+        double dmax = 0.0;
+        for (int j = 0; j < k; ++j) dmax = fmax(dmax, L[j * ld + j]);
+        s_floor = fmax(dmax * 1e-26, 1e-300);
+    }
+    __syncthreads();
+    const double floor_ = s_floor;
     for (int j = 0; j < k; ++j) {
-        double sacc = 0.0;
-        if (i < k && i >= j) {
-            double a0 = L[i * ld + j], a1 = 0.0, a2 = 0.0, a3 = 0.0;     // lower triangle still holds C
-            const double *li = L + i * ld, *lj = L + j * ld;
-            int q = 0;
-            for (; q + 4 <= j; q += 4) {
-                a0 -= li[q] * lj[q]; a1 -= li[q + 1] * lj[q + 1]; a2 -= li[q + 2] * lj[q + 2]; a3 -= li[q + 3] * lj[q + 3];
-            }
-            for (; q < j; ++q) a0 -= li[q] * lj[q];
-            sacc = (a0 + a1) + (a2 + a3);
-            if (i == j) {
-                if (!(sacc > floor_)) sacc = floor_;
-                L[j * ld + j] = sqrt(sacc);
-            }
+        double piv = L[j * ld + j];
+        if (!(piv > floor_)) piv = floor_;
+        const double inv = 1.0 / sqrt(piv);
+        __syncthreads();                                         // everyone has read the pivot
+        for (int i = j + tid; i < k; i += 256) L[i * ld + j] = (i == j) ? sqrt(piv) : L[i * ld + j] * inv;
+        __syncthreads();
+        for (int i = j + 1 + warp; i < k; i += 8) {              // trailing update, lower triangle only
+            const double lij = L[i * ld + j];
+            for (int q = j + 1 + lane; q <= i; q += 32) L[i * ld + q] -= lij * L[q * ld + j];
         }
         __syncthreads();
-        if (i < k && i > j) L[i * ld + j] = sacc / L[j * ld + j];
-        __syncthreads();
     }
-    for (int idx = i; idx < k * k; idx += 128) {
+    for (int idx = tid; idx < k * k; idx += 256) {
         const int r = idx / k, q = idx % k;
         Lout[idx] = (q <= r) ? L[r * ld + q] : 0.0;
     }
@@ -1111,7 +1109,7 @@ static int cholqr2_rows(const LanczosWs &lw, double *RT, double *out, int k, int
         set_t = smem_t;
     }
     if (int r = dgemm<false, true>(k, k, d, 1.0, RT, d, RT, d, 0.0, lw.C, k, st)) return r;             // C = R R^T
-    chol_kernel<<<1, 128, smem_c, st>>>(lw.C, k, lw.Linv);                                             // Linv holds L
+    chol_kernel<<<1, 256, smem_c, st>>>(lw.C, k, lw.Linv);                                             // Linv holds L
     GSB_CHECK_LAUNCH();
     trsm_rows_kernel<<<(unsigned)((d + TRSM_THREADS - 1) / TRSM_THREADS), TRSM_THREADS, smem_t, st>>>(lw.Linv, k, RT, d, out);
     GSB_CHECK_LAUNCH();
