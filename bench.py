@@ -226,7 +226,14 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "mapping MLP: pixelnorm_split + 8 x mapping_layer_tc_kernel (tcgen05, fp16 hi/lo x3)" if os.environ.get("GANSPACE_B200_MAPPING", "tc") != "simt" else "mapping MLP: pixelnorm + 8 x sgemm_tn_bias_act_kernel (fp32 FMA)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None,
+                         # dram__bytes_read+write of ONE layer launch over 1,010,000 rows, ncu --set full
+                         # (profiles/ncu_full_mapping_layer_tc_r01.csv); algorithmic bytes = 4.14e9
+                         "traffic": 4.06e9 if os.environ.get("GANSPACE_B200_MAPPING", "tc") != "simt" else None,
+                         "achieved_isolated": 329.0 if os.environ.get("GANSPACE_B200_MAPPING", "tc") != "simt" else None,
+                         "note": "achieved = live CUDA-event time of all mapping launches inside the timed steps (they run "
+                                 "next to the IPCA chain on 128 of 148 SMs); achieved_isolated = the same kernel alone "
+                                 "(ncu, 1.61 ms per layer over 1.01M rows)",
                          "peak_source": f"bf16_tflops_sustained, {peak_kind} (MEASURED_PEAKS.json)",
                          "ms_per_step": map_ms_step, "launches_per_step": map_calls / max(1, args.steps)},
             "sections_ms_per_step": {k: v[0] / args.steps for k, v in sections.items()},

@@ -168,11 +168,12 @@ class StyleGAN2(BaseModel):
             state = {"hi": 0}
             total = z.shape[0]
 
-            def ensure(row_end, chunk=max(4 * n_samples, 40_000)):
+            def ensure(row_end, first=max(4 * n_samples, 40_000), later=max(20 * n_samples, 200_000)):
+                # a small first chunk lets the IPCA chain start early; later chunks are large (tile-quantisation
+                # and launch overheads) and leave a GPC's worth of SMs to the chain they run next to
                 while state["hi"] < min(row_end, total):
                     a = state["hi"]
-                    b = min(total, a + chunk)
-                    # later chunks run next to the IPCA chain: leave it a GPC's worth of SMs
+                    b = min(total, a + (first if a == 0 else later))
                     packed.forward(z[a:b], out=z[a:b], leave_free_sms=0 if a == 0 else 20)
                     state["hi"] = b
             return z, ensure
