@@ -168,13 +168,17 @@ class StyleGAN2(BaseModel):
             state = {"hi": 0}
             total = z.shape[0]
 
-            def ensure(row_end, first=max(4 * n_samples, 40_000), later=max(20 * n_samples, 200_000)):
+            first_rows = int(os.environ.get("GANSPACE_B200_LAZY_FIRST", max(4 * n_samples, 40_000)))
+            later_rows = int(os.environ.get("GANSPACE_B200_LAZY_LATER", max(10 * n_samples, 100_000)))
+            free_sms = int(os.environ.get("GANSPACE_B200_LAZY_FREE_SMS", 48))   # tools/sweep_lazy.sh
+
+            def ensure(row_end, first=first_rows, later=later_rows):
                 # a small first chunk lets the IPCA chain start early; later chunks are large (tile-quantisation
                 # and launch overheads) and leave a GPC's worth of SMs to the chain they run next to
                 while state["hi"] < min(row_end, total):
                     a = state["hi"]
                     b = min(total, a + (first if a == 0 else later))
-                    packed.forward(z[a:b], out=z[a:b], leave_free_sms=0 if a == 0 else 20)
+                    packed.forward(z[a:b], out=z[a:b], leave_free_sms=0 if a == 0 else free_sms)
                     state["hi"] = b
             return z, ensure
         return self.model.style(z) if out is None else self.model.style.packed().forward(z, out=z)
