@@ -258,7 +258,7 @@ tridiag_kernel(const double *__restrict__ A, int n, double *__restrict__ dg, dou
 // Register-resident variant of the cluster tridiagonalisation (n <= 512, n % 16 == 0).
 // The shared-memory variants above spend their time on shared-memory bandwidth (every matrix element
 // is read and written once per reflector, plus three vector operands).  Here the CTA's column block
-// lives in REGISTERS: thread (warp w, lane l) owns row i = 16 l + w of the CTA's <= 32 columns
+// lives in REGISTERS: thread (warp w, lane l) owns row i = nw l + w (nw = 16 or 8 warps) of the CTA's <= 32 columns
 // j = me + 16 c.  Per reflector a thread applies the pending rank-2 update to its 32 elements with the
 // column operands broadcast from shared memory, the per-column sums are formed by a 31-shuffle
 // transpose-reduce inside each warp and a 16-way add across warps, and all row-indexed vector work
@@ -275,7 +275,8 @@ tridiag_reg_kernel(const double *__restrict__ A, int n, double *__restrict__ dg,
     __shared__ double red[64];
     const int me = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nc = n / TRI_CLUSTER;             // active columns of this CTA
-    const int i = 16 * lane + warp;             // own row
+    const int nw = blockDim.x >> 5;             // 16 warps (n <= 512) or 8 warps (n <= 256): one row per thread
+    const int i = nw * lane + warp;             // own row
     const bool row_ok = i < n;
 
     double Areg[TRR_NC];
@@ -286,7 +287,7 @@ tridiag_reg_kernel(const double *__restrict__ A, int n, double *__restrict__ dg,
     }
     double a_i = row_ok ? A[i] : 0.0;            // pivot column 0 (row 0 of A), own row
     double pv_i = 0.0, pw_i = 0.0;
-    pvw[tid] = make_double2(0.0, 0.0);
+    for (int q = tid; q < 512; q += blockDim.x) pvw[q] = make_double2(0.0, 0.0);
     if (me == 0 && tid == 0) dg[0] = A[0];
     __syncthreads();
 
@@ -312,7 +313,7 @@ tridiag_reg_kernel(const double *__restrict__ A, int n, double *__restrict__ dg,
         __syncthreads();
         if (me == 0) {
             if (tid == 0) { e[k] = alpha; beta[k] = bk; }
-            if (tid < n) Vh[(size_t)k * n + tid] = vsh[tid];
+            for (int q = tid; q < n; q += blockDim.x) Vh[(size_t)k * n + q] = vsh[q];
         }
         // ---- 2. pending rank-2 update + this CTA's share of (A v)_i, row-wise (A is symmetric) ----------
         // columns j = me + 16 c with j > k are live:  c0 <= c < nc
@@ -834,6 +835,7 @@ static int eig_top(const Workspace &w, int d, int c, double *evals, double *evec
         }
         if (reg_variant && d <= 512) {
             cfg.dynamicSmemBytes = 0;
+            if (d <= 256) cfg.blockDim = dim3(256);          // one row per thread: 8 warps suffice, cheaper barriers
             GSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tridiag_reg_kernel, (const double *)w.A, d, w.dg, w.e, w.beta, w.Vh,
                                               w.xch, w.qx));
         } else {
