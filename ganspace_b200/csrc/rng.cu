@@ -26,13 +26,13 @@ namespace gsb {
 
 constexpr int MT_N = 624;
 constexpr int MT_M = 397;
-constexpr int RNG_THREADS = 768;
+constexpr int RNG_THREADS = 1024;
 constexpr int RNG_PRODUCERS = 256;                         // warps 0-7
 constexpr int RNG_CONSUMERS = RNG_THREADS - RNG_PRODUCERS; // warps 8-31
 constexpr int BLOCKS_PER_SUPER = 16;
 constexpr int WORDS_PER_SUPER = MT_N * BLOCKS_PER_SUPER;   // 9984
 constexpr int ATT_PER_SUPER = WORDS_PER_SUPER / 4;         // 2496 polar attempts
-constexpr int ATT_PER_THREAD = 5;                          // 512*5 >= 2496
+constexpr int ATT_PER_THREAD = 4;                          // 768*4 >= 2496
 
 enum { MODE_RAW = 0, MODE_NORMAL = 1, MODE_TRUNCNORM = 2 };
 enum { BAR_FULL0 = 1, BAR_FULL1 = 2, BAR_EMPTY0 = 3, BAR_EMPTY1 = 4, BAR_PROD = 5, BAR_CONS = 6 };
