@@ -215,3 +215,37 @@ def test_linreg_accumulate_solve(nat):
     M, zmean = acc.solve()
     assert np.max(np.abs(M.cpu().numpy() - M_ref)) < 1e-5
     assert np.allclose(zmean.cpu().numpy(), Z.mean(axis=0), atol=1e-6)
+
+
+def test_estimator_accepts_host_arrays_and_cuda_tensors(golden):
+    """IPCAEstimator keeps the reference's ndarray interface (estimators.py:68-81) and takes CUDA tensors as is."""
+    from ganspace_b200.estimators import get_estimator
+    g = golden("ipca_chain_d96_c12.npz")
+    Xs = g["X"]
+    e_host, e_dev = get_estimator("ipca", 12, 1.0), get_estimator("ipca", 12, 1.0)
+    for X in Xs:
+        assert e_host.fit_partial(X.copy())                       # float32 ndarray, copied to the device
+        assert e_dev.fit_partial(torch.tensor(X).cuda())          # stays in HBM
+    ch, sh, rh = e_host.get_components()
+    cd, sd, rd = e_dev.get_components()
+    assert isinstance(ch, np.ndarray) and ch.shape == (12, 96) and ch.dtype == np.float64
+    assert np.allclose(ch, cd, atol=1e-9) and np.allclose(sh, sd, rtol=1e-9) and np.allclose(rh, rd, atol=1e-12)
+    k = Xs.shape[0] - 1
+    assert np.min(np.sum(ch * g[f"comp_{k}"], axis=1)) > 1 - 1e-6
+    assert int(e_host.transformer.n_samples_seen_) == Xs.shape[0] * Xs.shape[1]
+    assert e_host.transformer.mean_.shape == (96,)
+    # first batch smaller than n_components: sklearn raises ValueError -> fit_partial reports False
+    assert get_estimator("ipca", 12, 1.0).fit_partial(Xs[0][:5].copy()) is False
+
+
+def test_estimator_fit_runs_sklearn_batching(golden):
+    from ganspace_b200.estimators import get_estimator
+    from sklearn.decomposition import IncrementalPCA
+    g = golden("ipca_chain_d96_c12.npz")
+    X = np.concatenate(list(g["X"]), axis=0)
+    est = get_estimator("ipca", 12, 1.0)
+    est.fit(X)
+    ref = IncrementalPCA(12, whiten=False, batch_size=max(100, 24)).fit(X)
+    comp, stdev, ratio = est.get_components()
+    assert np.min(np.sum(comp * ref.components_, axis=1)) > 1 - 1e-6
+    assert np.allclose(stdev, np.sqrt(ref.explained_variance_), rtol=2e-5)
