@@ -44,7 +44,25 @@ SIGNATURES = {
     "gsb_linreg_workspace_bytes": (_Z, [_L, _I]),
     "gsb_linreg_accumulate": (_I, [_P, _I, _I, _P, _L, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "gsb_linreg_solve": (_I, [_P, _I, _I, _L, _P, _P, _P]),
+    "gsb_synthesis_packed_bytes": (_Z, [_P, _I, _I]),
+    "gsb_synthesis_pack": (_I, [_P, _I, _I, _P, _P, _Z, _P]),
+    "gsb_synthesis_workspace_bytes": (_Z, [_P, _I, _L]),
+    "gsb_synthesis_forward": (_I, [_P, _P, _I, _I, _I, _P, _L, _P, _L, _P, _Z, _P]),
+    "gsb_synthesis_status": (_I, [_P, _P, _I, _I, _P]),
+    "gsb_bigd_rows": (_I, [_I, _I]),
+    "gsb_bigd_state_bytes": (_Z, [_L, _I]),
+    "gsb_bigd_workspace_bytes": (_Z, [_L, _I, _I]),
+    "gsb_bigd_reset": (_I, [_P, _P, _L, _I, _I, _P]),
+    "gsb_bigd_chain_step": (_I, [_P, _P, _L, _I, _I, _L, _I, _P, _P, _Z, _P]),
+    "gsb_bigd_export": (_I, [_P, _P, _L, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
 }
+
+
+class StyledConvDesc(C.Structure):
+    """``gsb_styled_conv`` of include/ganspace_b200.h (device pointers to the module's fp32 parameters)."""
+    _fields_ = [("conv_weight", C.c_void_p), ("mod_weight", C.c_void_p), ("mod_bias", C.c_void_p),
+                ("act_bias", C.c_void_p), ("noise", C.c_void_p), ("noise_weight", C.c_void_p),
+                ("cin", C.c_int), ("cout", C.c_int), ("upsample", C.c_int), ("res_in", C.c_int)]
 
 
 class NativeError(RuntimeError):
@@ -448,3 +466,133 @@ class LinregAccumulator:
                    "gsb_linreg_solve")
         instrument.count(1)
         return M, zmean
+
+
+class PackedSynthesis:
+    """StyleGAN2 synthesis layers conv1, convs.0 .. convs.k packed for the tap-GEMM kernels (gsb_synthesis_pack).
+
+    ``layers``: dicts with conv_weight [co,ci,3,3], mod_weight [ci,S], mod_bias [ci], act_bias [co], noise [r,r],
+    noise_weight [1] (fp32 CUDA tensors) and upsample (bool), res_in (int), in execution order."""
+
+    def __init__(self, const_input: torch.Tensor, layers, style_dim: int):
+        lib = load()
+        self.device = require_cuda(const_input.device)
+        self.style_dim = int(style_dim)
+        self.n_layers = len(layers)
+        self._keep = []
+        self.desc = (StyledConvDesc * self.n_layers)()
+        self.shapes = []                        # (res_out, cout) per layer
+        f32 = lambda t: t.detach().to(self.device, torch.float32).contiguous()
+        for i, L in enumerate(layers):
+            ts = {k: f32(L[k]) for k in ("conv_weight", "mod_weight", "mod_bias", "act_bias", "noise", "noise_weight")}
+            self._keep.append(ts)
+            co, ci = ts["conv_weight"].shape[0], ts["conv_weight"].shape[1]
+            assert ts["conv_weight"].shape == (co, ci, 3, 3) and ts["mod_weight"].shape == (ci, self.style_dim)
+            res_in, up = int(L["res_in"]), bool(L["upsample"])
+            res_out = 2 * res_in if up else res_in
+            assert ts["noise"].numel() == res_out * res_out and ts["noise_weight"].numel() == 1
+            d = self.desc[i]
+            for k, t in ts.items():
+                setattr(d, k, t.data_ptr())
+            d.cin, d.cout, d.upsample, d.res_in = ci, co, int(up), res_in
+            self.shapes.append((res_out, co))
+        cst = f32(const_input).reshape(-1, 4, 4)
+        nbytes = lib.gsb_synthesis_packed_bytes(self.desc, self.n_layers, self.style_dim)
+        if nbytes == 0:
+            raise NativeError(f"gsb_synthesis_packed_bytes: {lib.gsb_last_error().decode()}")
+        self.packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(lib.gsb_synthesis_pack(self.desc, self.n_layers, self.style_dim, _ptr(cst), _ptr(self.packed),
+                                          self.packed.numel(), _stream()), "gsb_synthesis_pack")
+            torch.cuda.current_stream().synchronize()      # the temporaries above may be freed after this returns
+
+    def out_dims(self, n_run: int) -> int:
+        r, co = self.shapes[n_run - 1]
+        return r * r * co
+
+    def forward(self, w: torch.Tensor, n_run: int, out: torch.Tensor = None) -> torch.Tensor:
+        """Activation of layer ``n_run - 1`` for w[n, style_dim]: fp32 NHWC rows [n, res*res*cout] (``out`` may be a
+        row-strided 2-D view, e.g. the batch rows of the large-d IPCA buffer)."""
+        lib = load()
+        assert w.is_cuda and w.dtype == torch.float32 and w.dim() == 2 and w.shape[1] == self.style_dim
+        w = w.contiguous()
+        n, d = w.shape[0], self.out_dims(n_run)
+        if out is None:
+            out = torch.empty((n, d), dtype=torch.float32, device=w.device)
+        assert out.is_cuda and out.dtype == torch.float32 and out.shape == (n, d) and out.stride(1) == 1
+        ws_bytes = lib.gsb_synthesis_workspace_bytes(self.desc, n_run, n)
+        ws = scratch.get("synthesis", ws_bytes, w.device)
+        with torch.cuda.device(w.device), instrument.section("synthesis"):
+            _check(lib.gsb_synthesis_forward(_ptr(self.packed), self.desc, self.n_layers, n_run, self.style_dim, _ptr(w), n,
+                                             C.c_void_p(out.data_ptr()), out.stride(0), _ptr(ws), ws.numel(), _stream()),
+                   "gsb_synthesis_forward")
+        # per layer: 4 style/demod launches; per chunk of samples: 1 GEMM + 1 (stride-1) or 2 (upsample) epilogue launches
+        launches = 1
+        for i in range(n_run):
+            res_in = self.desc[i].res_in
+            chunks = -(-n // max(1, 4096 // (res_in * res_in)))
+            launches += 4 + chunks * (3 if self.desc[i].upsample else 2)
+        instrument.count(launches)
+        return out
+
+    def check(self):
+        flags = C.c_uint(0)
+        with torch.cuda.device(self.device):
+            _check(load().gsb_synthesis_status(_ptr(self.packed), self.desc, self.n_layers, self.style_dim, C.byref(flags)),
+                   "gsb_synthesis_status")
+        if flags.value & 1:
+            raise NativeError("synthesis: an operand exceeded fp16 range in the tensor-core path; results are invalid")
+
+
+class BigIPCA:
+    """Large-d IncrementalPCA engine (csrc/bigd.cu): the stacked matrix M = [S*Vt; batch; correction] lives in HBM,
+    producers write the batch rows in place (``batch_rows``), ``step`` runs one partial_fit."""
+
+    def __init__(self, d: int, c: int, nb_max: int, device):
+        lib = load()
+        self.dev = require_cuda(device)
+        self.d, self.c, self.nb_max = int(d), int(c), int(nb_max)
+        ws_bytes = lib.gsb_bigd_workspace_bytes(self.d, self.c, self.nb_max)
+        if ws_bytes == 0:
+            raise NativeError(f"gsb_bigd_workspace_bytes: {lib.gsb_last_error().decode()}")
+        self.rows = lib.gsb_bigd_rows(self.c, self.nb_max)
+        self.M = torch.empty((self.rows, self.d), dtype=torch.float32, device=self.dev)
+        self.state = torch.empty(lib.gsb_bigd_state_bytes(self.d, self.c), dtype=torch.uint8, device=self.dev)
+        self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.dev)
+        self.batch_mean = torch.zeros(self.d, dtype=torch.float64, device=self.dev)
+        self.n_seen = 0
+        self.last_nb = 0
+        with torch.cuda.device(self.dev):
+            _check(lib.gsb_bigd_reset(_ptr(self.state), _ptr(self.M), self.d, self.c, self.nb_max, _stream()), "gsb_bigd_reset")
+
+    def batch_rows(self, nb: int) -> torch.Tensor:
+        assert 1 <= nb <= self.nb_max
+        return self.M[self.c:self.c + nb]
+
+    def step(self, nb: int):
+        lib = load()
+        with torch.cuda.device(self.dev), instrument.section("chain"):
+            _check(lib.gsb_bigd_chain_step(_ptr(self.state), _ptr(self.M), self.d, self.c, self.nb_max, self.n_seen, int(nb),
+                                           _ptr(self.batch_mean), _ptr(self.ws), self.ws.numel(), _stream()),
+                   "gsb_bigd_chain_step")
+        lanczos = self.n_seen > 0 and self.c % 16 == 0 and self.c <= 128 and 3 * self.c <= self.rows // 2 + self.rows // 8
+        instrument.count(6 + (37 if lanczos else 5))
+        self.n_seen += int(nb)
+        self.last_nb = int(nb)
+
+    def export(self):
+        lib = load()
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        out = {
+            "components": torch.empty((self.c, self.d), dtype=torch.float32, device=self.dev),
+            "singular_values": torch.empty(self.c, **f64), "mean": torch.empty(self.d, **f64),
+            "var": torch.empty(self.d, **f64), "explained_variance": torch.empty(self.c, **f64),
+            "explained_variance_ratio": torch.empty(self.c, **f64),
+        }
+        with torch.cuda.device(self.dev):
+            _check(lib.gsb_bigd_export(_ptr(self.state), _ptr(self.M), self.d, self.c, self.n_seen, _ptr(out["components"]),
+                                       _ptr(out["singular_values"]), _ptr(out["mean"]), _ptr(out["var"]),
+                                       _ptr(out["explained_variance"]), _ptr(out["explained_variance_ratio"]), _stream()),
+                   "gsb_bigd_export")
+        instrument.count(3)
+        return out

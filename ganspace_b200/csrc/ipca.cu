@@ -15,7 +15,7 @@
 //   2. bisect_kernel    top-c eigenvalues of T by 32-way multisection (one warp per eigenvalue, Sturm counts).
 //   3. invit_kernel     eigenvectors of T by inverse iteration on the pivoted LU of T - lambda I.
 //   4. backtransform_kernel  applies the reflectors (one warp per eigenvector) and the sign rule.
-#include "common.cuh"
+#include "ipca_internal.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -37,13 +37,7 @@ __host__ __device__ inline StateView state_view(void *p, int d, int c) {
     return s;
 }
 
-struct Workspace {
-    double *A, *dg, *e, *beta, *Vh, *lam, *Z, *lu, *xch, *evecs, *qx;
-    unsigned *counter;
-    unsigned char *swp;
-    size_t bytes;
-};
-static Workspace carve(void *base, int d, int c) {
+Workspace carve(void *base, int d, int c) {
     Workspace w;
     char *p = reinterpret_cast<char *>(base);
     size_t off = 0;
@@ -252,6 +246,120 @@ tridiag_kernel(const double *__restrict__ A, int n, double *__restrict__ dg, dou
         int l = (n - 1) / P;
         dg[n - 1] = Aloc[(size_t)l * n + (n - 1)] - 2.0 * pv[n - 1] * pw[n - 1];
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// L2-resident variant for 1024 < n <= 4096 (the small side of the large-d engine, n = c + NB + 1 ~ 2100): the
+// matrix (n^2 fp64 = 36 MB at n = 2112) does not fit the shared memory of the machine but sits in the 126 MB L2.
+// Same algorithm and exchange as tridiag_kernel<false> (one software grid barrier per reflector); the owned
+// columns j = me + P l are updated IN PLACE in global memory (row j of the symmetric input == column j), one warp
+// per column, four independent 256-byte segments in flight per lane.  P ~ n/16 co-resident CTAs of 16 warps.
+// ---------------------------------------------------------------------------------------------
+constexpr int TRL_THREADS = 512;
+__global__ void __launch_bounds__(TRL_THREADS, 1)
+tridiag_l2_kernel(double *__restrict__ A, int n, double *__restrict__ dg, double *__restrict__ e,
+                  double *__restrict__ beta, double *__restrict__ Vh, double *__restrict__ xch,
+                  unsigned *__restrict__ counter) {
+    extern __shared__ double smd[];
+    const int P = gridDim.x, me = blockIdx.x, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = TRL_THREADS / 32;
+    const int ncl = (n + P - 1) / P;
+    double *a = smd;                  // current pivot column (rows > k valid)
+    double *v = a + n;
+    double *w = v + n;
+    double *pv = w + n;               // pending rank-2 update (v_{k-1}, w_{k-1})
+    double *pw = pv + n;
+    double *red = pw + n;             // [64]
+
+    for (int i = tid; i < n; i += TRL_THREADS) {
+        a[i] = A[i];                  // column 0 (never modified: only columns j > k are touched)
+        pv[i] = 0.0;
+        pw[i] = 0.0;
+        w[i] = 0.0;
+    }
+    if (me == 0 && tid == 0) dg[0] = A[0];
+    __syncthreads();
+
+    unsigned target = 0;
+    for (int k = 0; k <= n - 3; ++k) {
+        const int par = k & 1;
+        double *Pbuf = xch + (size_t)par * 2 * n, *Rbuf = Pbuf + n;
+        // ---- 1. reflector from a[k+1 .. n-1] (redundant in every CTA) ---------------------------
+        const double x0 = a[k + 1];
+        double part = 0.0;
+        for (int i = k + 2 + tid; i < n; i += TRL_THREADS) part += a[i] * a[i];
+        const double sigma = block_sum(part, red);
+        double alpha, bk, v0;
+        if (sigma == 0.0) {
+            alpha = x0; bk = 0.0; v0 = 0.0;
+        } else {
+            const double nrm = sqrt(x0 * x0 + sigma);
+            alpha = (x0 > 0.0) ? -nrm : nrm;
+            v0 = x0 - alpha;
+            bk = 1.0 / (nrm * (nrm + fabs(x0)));     // 2 / (v^T v)
+        }
+        for (int i = tid; i < n; i += TRL_THREADS)
+            v[i] = (i <= k || bk == 0.0) ? 0.0 : ((i == k + 1) ? v0 : a[i]);
+        __syncthreads();
+        if (me == 0) {
+            if (tid == 0) { e[k] = alpha; beta[k] = bk; }
+            for (int i = tid; i < n; i += TRL_THREADS) Vh[(size_t)k * n + i] = v[i];
+        }
+        // ---- 2. fused pass over the owned columns: pending update, p = A v, next pivot row ---------
+        for (int l = warp; l < ncl; l += nwarps) {
+            const int j = me + P * l;
+            if (j >= n || j <= k) continue;
+            double *col = A + (size_t)j * n;
+            const double pvj = pv[j], pwj = pw[j];
+            double acc = 0.0, rj = 0.0;
+            int i = k + 1 + lane;
+            for (; i + 96 < n; i += 128) {
+                const double c0 = col[i], c1 = col[i + 32], c2 = col[i + 64], c3 = col[i + 96];
+                const double x0_ = c0 - pv[i] * pwj - pw[i] * pvj;
+                const double x1_ = c1 - pv[i + 32] * pwj - pw[i + 32] * pvj;
+                const double x2_ = c2 - pv[i + 64] * pwj - pw[i + 64] * pvj;
+                const double x3_ = c3 - pv[i + 96] * pwj - pw[i + 96] * pvj;
+                col[i] = x0_; col[i + 32] = x1_; col[i + 64] = x2_; col[i + 96] = x3_;
+                acc += x0_ * v[i] + x1_ * v[i + 32] + x2_ * v[i + 64] + x3_ * v[i + 96];
+                if (i == k + 1) rj = x0_;
+            }
+            for (; i < n; i += 32) {
+                const double x = col[i] - pv[i] * pwj - pw[i] * pvj;
+                col[i] = x;
+                acc += x * v[i];
+                if (i == k + 1) rj = x;
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) {                    // lane 0 owns row k+1 (i starts at k+1+lane)
+                __stcg(&Pbuf[j], bk * acc);
+                __stcg(&Rbuf[j], rj);
+            }
+        }
+        // ---- 3. exchange ---------------------------------------------------------------------
+        target += (unsigned)P;
+        grid_barrier(counter, target);
+        // ---- 4. w, next pivot column (redundant in every CTA) -------------------------------------
+        part = 0.0;
+        for (int i = k + 1 + tid; i < n; i += TRL_THREADS) {
+            double pi = __ldcg(&Pbuf[i]);
+            w[i] = pi;
+            a[i] = __ldcg(&Rbuf[i]);
+            part += pi * v[i];
+        }
+        const double ptv = block_sum(part, red);
+        const double K2 = 0.5 * bk * ptv;
+        for (int i = k + 1 + tid; i < n; i += TRL_THREADS) w[i] -= K2 * v[i];
+        __syncthreads();
+        const double vk1 = v[k + 1], wk1 = w[k + 1];
+        for (int i = k + 1 + tid; i < n; i += TRL_THREADS) a[i] -= vk1 * w[i] + wk1 * v[i];
+        __syncthreads();
+        if (me == 0 && tid == 0) dg[k + 1] = a[k + 1];
+        double *t = pv; pv = v; v = t;
+        t = pw; pw = w; w = t;
+    }
+    if (me == 0 && tid == 0) { e[n - 2] = a[n - 1]; e[n - 1] = 0.0; beta[n - 2] = 0.0; beta[n - 1] = 0.0; }
+    if (me == (n - 1) % P && tid == 0)
+        dg[n - 1] = A[(size_t)(n - 1) * n + (n - 1)] - 2.0 * pv[n - 1] * pw[n - 1];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -477,7 +585,7 @@ invit_kernel(const double *__restrict__ dg, const double *__restrict__ e, const 
              int c, double *__restrict__ Z) {
     extern __shared__ double smd[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = blockIdx.x * IV_WARPS + warp;
+    const int t = blockIdx.x * (blockDim.x >> 5) + warp;      // 4 warps per CTA, 1 when n > 1024 (shared memory)
     if (t >= c) return;
     double *u0i = smd + (size_t)warp * (5 * (size_t)n + (size_t)(n + 7) / 8);   // 1/pivot
     double *u1 = u0i + n, *u2 = u1 + n, *ml = u2 + n, *xb = ml + n;
@@ -721,6 +829,46 @@ backtransform_kernel(const double *__restrict__ Z, const double *__restrict__ Vh
     }
 }
 
+// n > 1024: the eigenvector does not fit a warp's registers.  One CTA per eigenvector, z in shared memory, the
+// reflectors stream from L2; one block reduction per reflector (used once per large-d run, in the cold first step).
+__global__ void __launch_bounds__(256)
+backtransform_big_kernel(const double *__restrict__ Z, const double *__restrict__ Vh, const double *__restrict__ beta,
+                         int n, int c, double *__restrict__ out) {
+    extern __shared__ double smd[];
+    double *z = smd, *red = smd + n;                       // red[64]
+    const int tid = threadIdx.x, t = blockIdx.x;
+    for (int i = tid; i < n; i += 256) z[i] = Z[(size_t)t * n + i];
+    __syncthreads();
+    for (int k = n - 3; k >= 0; --k) {
+        const double bk = beta[k];
+        if (bk == 0.0) continue;
+        const double *vk = Vh + (size_t)k * n;
+        double vr[16];                                     // n <= 4096
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int i = k + 1 + tid + 256 * r;
+            vr[r] = (i < n) ? vk[i] : 0.0;
+            s += (i < n) ? vr[r] * z[i] : 0.0;
+        }
+        s = block_sum(s, red) * bk;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int i = k + 1 + tid + 256 * r;
+            if (i < n) z[i] -= s * vr[r];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {                                        // svd_flip sign rule: first largest |z| positive
+        double best = -1.0, bval = 0.0;
+        for (int i = 0; i < n; ++i) { const double az = fabs(z[i]); if (az > best) { best = az; bval = z[i]; } }
+        red[40] = (bval < 0.0) ? -1.0 : 1.0;
+    }
+    __syncthreads();
+    const double sgn = red[40];
+    for (int i = tid; i < n; i += 256) out[(size_t)t * n + i] = sgn * z[i];
+}
+
 template <int NR>
 static int launch_backtransform(const double *Z, const double *Vh, const double *beta, int d, int c, double *evecs,
                                 cudaStream_t st) {
@@ -786,7 +934,11 @@ __global__ void export_kernel(const double *hdr, const double *mean, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-static int eig_top(const Workspace &w, int d, int c, double *evals, double *evecs, cudaStream_t st) {
+static int eig_top_big(const Workspace &w, int d, int c, double *evals, double *evecs, cudaStream_t st);
+static size_t g_iv_smem_set = 0, g_bis_smem_set = 0;     // largest dynamic-smem opt-in made so far (shared by both paths)
+
+int eig_top(const Workspace &w, int d, int c, double *evals, double *evecs, cudaStream_t st) {
+    if (d > 1024) return eig_top_big(w, d, c, evals, evecs, st);
     // Preferred: one 16-CTA cluster (hardware barrier) when the column blocks fit in shared memory.
     static int cluster_ok = -1;     // -1 unknown, 0 unavailable, 1 usable
     const size_t cl_smem = ((size_t)(d / TRI_CLUSTER) * d + 5 * (size_t)d + 64) * sizeof(double);
@@ -864,10 +1016,9 @@ static int eig_top(const Workspace &w, int d, int c, double *evals, double *evec
     bisect_kernel<<<c, BIS_THREADS, bis_smem, st>>>(w.dg, w.e, d, c, evals);
     GSB_CHECK_LAUNCH();
     const size_t iv_smem = (size_t)IV_WARPS * (5 * (size_t)d + (size_t)(d + 7) / 8) * sizeof(double);
-    static size_t iv_smem_set = 0;
-    if (iv_smem > iv_smem_set) {
+    if (iv_smem > g_iv_smem_set) {
         GSB_CHECK_CUDA(cudaFuncSetAttribute(invit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iv_smem));
-        iv_smem_set = iv_smem;
+        g_iv_smem_set = iv_smem;
     }
     invit_kernel<<<(c + IV_WARPS - 1) / IV_WARPS, IV_WARPS * 32, iv_smem, st>>>(w.dg, w.e, evals, d, c, w.Z);
     GSB_CHECK_LAUNCH();
@@ -878,6 +1029,49 @@ static int eig_top(const Workspace &w, int d, int c, double *evals, double *evec
     else if (d <= 256) { if (int r = launch_backtransform<8>(w.Z, w.Vh, w.beta, d, c, evecs, st)) return r; }
     else if (d <= 512) { if (int r = launch_backtransform<16>(w.Z, w.Vh, w.beta, d, c, evecs, st)) return r; }
     else { if (int r = launch_backtransform<32>(w.Z, w.Vh, w.beta, d, c, evecs, st)) return r; }
+    return GSB_OK;
+}
+
+// 1024 < d <= 4096: L2-resident tridiagonalisation, then the same bisection / inverse iteration (one warp per CTA:
+// the LU of T - lambda I takes 5 d doubles of shared memory) and the shared-memory back-transform.
+static int eig_top_big(const Workspace &w, int d, int c, double *evals, double *evecs, cudaStream_t st) {
+    GSB_CHECK_ARG(d % 32 == 0 && d <= 4096, "sym_eig: large variant needs d %% 32 == 0, d <= 4096 (d=%d)", d);
+    int P = (d + 15) / 16;                                  // one column per warp
+    const int maxp = num_sms() - 8;
+    if (P > maxp) P = maxp;
+    const size_t tri_smem = (5 * (size_t)d + 64) * sizeof(double);
+    const size_t bis_smem = (2 * (size_t)d + 64) * sizeof(double);
+    const size_t iv_smem = (5 * (size_t)d + (size_t)(d + 7) / 8) * sizeof(double);
+    const size_t bt_smem = ((size_t)d + 64) * sizeof(double);
+    static size_t tri_set = 0, bt_set = 0;
+    if (tri_smem > tri_set) {
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(tridiag_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem));
+        tri_set = tri_smem;
+    }
+    if (bis_smem > g_bis_smem_set && bis_smem > 48 * 1024) {
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bis_smem));
+        g_bis_smem_set = bis_smem;
+    }
+    if (iv_smem > g_iv_smem_set) {
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(invit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iv_smem));
+        g_iv_smem_set = iv_smem;
+    }
+    if (bt_smem > bt_set) {
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(backtransform_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem));
+        bt_set = bt_smem;
+    }
+    GSB_CHECK_CUDA(cudaMemsetAsync(w.counter, 0, 256, st));
+    tridiag_l2_kernel<<<P, TRL_THREADS, tri_smem, st>>>(w.A, d, w.dg, w.e, w.beta, w.Vh, w.xch, w.counter);
+    GSB_CHECK_LAUNCH();
+    bisect_kernel<<<c, BIS_THREADS, bis_smem, st>>>(w.dg, w.e, d, c, evals);
+    GSB_CHECK_LAUNCH();
+    invit_kernel<<<c, 32, iv_smem, st>>>(w.dg, w.e, evals, d, c, w.Z);
+    GSB_CHECK_LAUNCH();
+    const size_t co_smem = ((size_t)d + c + 64) * sizeof(double) + (size_t)c * sizeof(int);
+    cluster_orth_kernel<<<1, CO_THREADS, co_smem, st>>>(evals, w.dg, w.e, d, c, w.Z);
+    GSB_CHECK_LAUNCH();
+    backtransform_big_kernel<<<c, 256, bt_smem, st>>>(w.Z, w.Vh, w.beta, d, c, evecs);
+    GSB_CHECK_LAUNCH();
     return GSB_OK;
 }
 
@@ -1063,12 +1257,7 @@ __global__ void sign_rows_kernel(double *__restrict__ V, int c, int d) {
         for (int i = lane; i < d; i += 32) row[i] = -row[i];
 }
 
-struct LanczosWs {
-    double *QbT, *RT, *T, *C, *Linv, *WT, *H, *U, *lamH;
-    void *eig_ws;
-    size_t bytes;
-};
-static LanczosWs carve_lanczos(void *base, int d, int c) {
+LanczosWs carve_lanczos(void *base, int d, int c) {
     LanczosWs w;
     char *p = reinterpret_cast<char *>(base);
     size_t off = 0;
@@ -1087,7 +1276,7 @@ static LanczosWs carve_lanczos(void *base, int d, int c) {
     w.bytes = off;
     return w;
 }
-static bool lanczos_applicable(int d, int c) {
+bool lanczos_applicable(int d, int c) {
     static int enabled = -1;
     if (enabled == -1) {
         const char *env = getenv("GANSPACE_B200_CHAIN");
@@ -1128,8 +1317,8 @@ static int cholqr2_rows(const LanczosWs &lw, double *RT, double *out, int k, int
 }
 
 // top-c eigenpairs of the symmetric G[d,d] from the block Krylov space of the previous components Vprev[c,d]
-static int eig_top_lanczos(const LanczosWs &lw, const double *G, const double *Vprev, int d, int c, double *evals,
-                           double *evecs, cudaStream_t st) {
+int eig_top_lanczos(const LanczosWs &lw, const double *G, const double *Vprev, int d, int c, double *evals,
+                    double *evecs, cudaStream_t st) {
     const int kd = 3 * c;
     GSB_CHECK_CUDA(cudaMemcpyAsync(lw.QbT, Vprev, (size_t)c * d * sizeof(double), cudaMemcpyDeviceToDevice, st));
     for (int j = 0; j < 2; ++j) {
@@ -1240,7 +1429,7 @@ extern "C" int gsb_ipca_export(const void *d_state, int d, int c, int64_t n_seen
 extern "C" int gsb_sym_eig_top(double *d_a, int d, int c, double *d_evals, double *d_evecs,
                                void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
     GSB_CHECK_ARG(d_a && d_evals && d_evecs && d_workspace, "sym_eig_top: null pointer");
-    if (int r = gsb::check_dims(d, c)) return r;
+    GSB_CHECK_ARG(d >= 32 && d <= 4096 && d % 32 == 0 && c >= 1 && c <= d, "sym_eig_top: need 32 <= d <= 4096, d%%32==0, 1 <= c <= d");
     gsb::Workspace w = gsb::carve(d_workspace, d, c);
     if (workspace_bytes < w.bytes) {
         gsb::set_error("sym_eig_top: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);

@@ -126,6 +126,7 @@ struct TcParams {
     unsigned *overflow;     // set to 1 when an activation leaves fp16's range
     const float *inv_wscale;   // device pointer to 2^-s of this layer
     int M, N_total, K;
+    int mode;               // 0: (acc 2^-s + bias) -> leaky-ReLU * sqrt2 (EqualLinear);  1: plain acc 2^-s (tc_gemm_plain)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -237,9 +238,13 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float x = __fmul_rn(__uint_as_float(v[j]), inv_wscale) + __ldg(&p.bias[n0 + c0 + j]);
-                    x = (x >= 0.f) ? x : __fmul_rn(x, 0.2f);
-                    f[j] = __fmul_rn(sqrt2, x);
+                    float x = __fmul_rn(__uint_as_float(v[j]), inv_wscale);
+                    if (p.mode == 0) {
+                        x += __ldg(&p.bias[n0 + c0 + j]);
+                        x = (x >= 0.f) ? x : __fmul_rn(x, 0.2f);
+                        x = __fmul_rn(sqrt2, x);
+                    }
+                    f[j] = x;
                 }
                 if (row < p.M) {
                     if (p.out_f32) {
@@ -429,6 +434,41 @@ int mapping_tc_pack(const float *pw, int n_layers, int dim, void *tc_base, cudaS
     return GSB_OK;
 }
 
+static int tc_ensure_attr() {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(mapping_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    return GSB_OK;
+}
+
+// out[M, N] (fp32, row-major) = (A_hi + A_lo)[M, K] * (W_hi + W_lo)[N, K]^T * inv_wscale   -- the same persistent
+// tcgen05 kernel with the plain epilogue.  Both operands are K-major fp16 hi/lo pairs; K % 64 == 0, N % 256 == 0.
+// Used by the modulated-convolution path (synthesis.cu): one dense contraction per 3x3 tap.
+int tc_gemm_plain(const __half *a_hi, const __half *a_lo, int64_t M, int K, const __half *w_hi, const __half *w_lo, int N,
+                  const float *inv_wscale, float *out, unsigned *overflow, int leave_free_sms, cudaStream_t st) {
+    GSB_CHECK_ARG(N % TC_BLOCK_N == 0 && K % TC_BLOCK_K == 0 && M > 0 && M < (1ll << 31),
+                  "tc_gemm_plain: need N%%256==0, K%%64==0 (M=%lld N=%d K=%d)", (long long)M, N, K);
+    if (int r = tc_ensure_attr()) return r;
+    CUtensorMap tm_ah, tm_al, tm_wh, tm_wl;
+    if (int r = make_tmap_f16(&tm_ah, a_hi, (uint64_t)M, (uint64_t)K, TC_BLOCK_M)) return r;
+    if (int r = make_tmap_f16(&tm_al, a_lo, (uint64_t)M, (uint64_t)K, TC_BLOCK_M)) return r;
+    if (int r = make_tmap_f16(&tm_wh, w_hi, (uint64_t)N, (uint64_t)K, TC_BLOCK_N)) return r;
+    if (int r = make_tmap_f16(&tm_wl, w_lo, (uint64_t)N, (uint64_t)K, TC_BLOCK_N)) return r;
+    TcParams p;
+    p.bias = nullptr; p.out_hi = nullptr; p.out_lo = nullptr; p.out_f32 = out; p.overflow = overflow;
+    p.inv_wscale = inv_wscale; p.M = (int)M; p.N_total = N; p.K = K; p.mode = 1;
+    const int num_tiles = (int)((M + TC_BLOCK_M - 1) / TC_BLOCK_M) * (N / TC_BLOCK_N);
+    int avail = num_sms() - leave_free_sms;
+    if (avail < 16) avail = 16;
+    mapping_layer_tc_kernel<<<num_tiles < avail ? num_tiles : avail, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_ah, tm_al, tm_wh,
+                                                                                                    tm_wl, p);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
 // Full mapping network on the tensor cores.  ws: 4 fp16 buffers of n*dim (two hi/lo ping-pong pairs).
 int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim,
                        const float *d_z, float *d_w, int64_t n, bool pixelnorm, void *ws, int leave_free_sms,
@@ -440,12 +480,7 @@ int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim,
     __half *a_hi[2] = {reinterpret_cast<__half *>(ws), reinterpret_cast<__half *>((char *)ws + 2 * buf)};
     __half *a_lo[2] = {reinterpret_cast<__half *>((char *)ws + buf), reinterpret_cast<__half *>((char *)ws + 3 * buf)};
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        GSB_CHECK_CUDA(cudaFuncSetAttribute(mapping_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)TC_SMEM_BYTES));
-        attr_set = true;
-    }
+    if (int r = tc_ensure_attr()) return r;
     pixelnorm_split_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(d_z, a_hi[0], a_lo[0], n, dim, pixelnorm ? 1 : 0,
                                                                   v.overflow);
     GSB_CHECK_LAUNCH();
@@ -471,7 +506,7 @@ int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim,
         p.out_f32 = last ? d_w : nullptr;
         p.overflow = v.overflow;
         p.inv_wscale = v.inv_wscale + l;
-        p.M = (int)n; p.N_total = dim; p.K = dim;
+        p.M = (int)n; p.N_total = dim; p.K = dim; p.mode = 0;
         mapping_layer_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_ah, tm_al, tm_wh, tm_wl, p);
         GSB_CHECK_LAUNCH();
     }

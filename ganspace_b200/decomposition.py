@@ -111,9 +111,11 @@ def _sample_batches_lazy(model, Bsz, seeds):
 
 
 # Solve for directions in latent space that match PCs in activation space (reference :77-139)
-def linreg_lstsq(comp_np, mean_np, stdev_np, inst, config, affine=None):
+def linreg_lstsq(comp_np, mean_np, stdev_np, inst, config, affine=None, native=False):
     """``affine``: when the hooked layer is affine in the latent (models/biggan.py AffineLayer), comp/mean are
-    given in its r-dimensional coordinates and the projections run there: (act-mean).comp^T == (y-ybar).comp_y^T."""
+    given in its r-dimensional coordinates and the projections run there: (act-mean).comp^T == (y-ybar).comp_y^T.
+    ``native``: comp/mean are given in the model's device feature order (``feature_layout``) and the activations
+    come from ``model.activations_into`` in that same order (no hook read-back, no permutation)."""
     print("Performing least squares regression", flush=True)
     torch.manual_seed(SEED_LINREG)
     np.random.seed(SEED_LINREG)
@@ -129,6 +131,7 @@ def linreg_lstsq(comp_np, mean_np, stdev_np, inst, config, affine=None):
     rank, world, live = _dist()
 
     acc = _native.LinregAccumulator(n_comp, latent_dims, dev)
+    act_buf = torch.empty((B, comp.shape[1]), dtype=torch.float32, device=dev) if native else None
     seeds = _draw_seeds(n_samp // B)
     group = max(1, min(len(seeds), (256 << 20) // max(1, B * latent_dims * 4)))
     for start in range(0, len(seeds), group):
@@ -140,6 +143,8 @@ def linreg_lstsq(comp_np, mean_np, stdev_np, inst, config, affine=None):
             z = z_all[j * B:(j + 1) * B]
             if affine is not None:
                 act = affine.coords(z.reshape(B, -1))
+            elif native:
+                act = model.activations_into(z, config.layer, act_buf)
             else:
                 with torch.no_grad():
                     model.partial_forward(z, config.layer)
@@ -154,12 +159,12 @@ def linreg_lstsq(comp_np, mean_np, stdev_np, inst, config, affine=None):
     return M_t.cpu().numpy()[:n_comp, :], Z_mean.cpu().numpy().reshape(1, -1)
 
 
-def regression(comp, mean, stdev, inst, config, affine=None):
+def regression(comp, mean, stdev, inst, config, affine=None, native=False):
     M = np.dot(comp, comp.T)
     if not np.allclose(M, np.identity(M.shape[0])):
         det = np.linalg.det(M)
         print(f"WARNING: Computed basis is not orthonormal (determinant={det})")
-    return linreg_lstsq(comp, mean, stdev, inst, config, affine=affine)
+    return linreg_lstsq(comp, mean, stdev, inst, config, affine=affine, native=native)
 
 
 def compute(config, dump_name, instrumented_model):
@@ -221,6 +226,21 @@ def compute_arrays(config, instrumented_model):
     transformer = get_estimator(config.estimator, config.components, config.sparsity, device=device)
     if not transformer.batch_support:
         raise RuntimeError("only batched estimators run on the device path")
+    samples_are_latents = layer_key in ["g_mapping", "style"] and inst.model.latent_space_name() == "W"
+    # conv feature maps (d up to ~10^6): the large-d IPCA engine keeps sklearn's stacked matrix in HBM and the model's
+    # producer kernels write each batch into it in the device feature order (NHWC); the fixed NHWC->NCHW permutation
+    # is applied once to the exported components (PCA is equivariant under it)
+    large_d = affine is None and not samples_are_latents and sample_dims > transformer.transformer.SMALL_D_MAX
+    layout = model.feature_layout(layer_key) if (large_d and hasattr(model, "feature_layout")) else None
+    if large_d and live:
+        raise NotImplementedError("large-d layers under torch.distributed need the feature-sharded chain "
+                                  "(SURVEY.md section 8e); run them on one GPU in this round")
+    if layout is not None:
+        lh, lw, lc = layout[1]
+        to_nchw = lambda A: np.ascontiguousarray(A.reshape(A.shape[0], lh, lw, lc).transpose(0, 3, 1, 2)).reshape(A.shape[0], -1)
+        to_native = lambda A: np.ascontiguousarray(A.reshape(A.shape[0], lc, lh, lw).transpose(0, 2, 3, 1)).reshape(A.shape[0], -1)
+    else:
+        to_nchw = to_native = lambda A: A
 
     B = config.batch_size or get_max_batch_size(inst, device, layer_key)
     pl = _plan.make_plan(config.n, B, config.components)
@@ -232,7 +252,6 @@ def compute_arrays(config, instrumented_model):
 
     # ---- Phase A: the seeds of every sample_latent(B) call the reference makes (:232-236) ----------
     seeds = _draw_seeds(pl.n_calls)
-    samples_are_latents = layer_key in ["g_mapping", "style"] and inst.model.latent_space_name() == "W"
 
     # ---- Phase B: per-group statistics + merge chain (:239-265) ------------------------------------
     K = pl.K
@@ -257,6 +276,20 @@ def compute_arrays(config, instrumented_model):
                     X = rows
                 elif affine is not None:
                     X = affine.coords(rows)
+                elif large_d:
+                    X = tr.batch_buffer(NB, d, device)              # rows of the engine's stacked matrix, in HBM
+                    for mb in range(0, NB, B):
+                        space_left = min(B, NB - mb)
+                        z = rows[mb:mb + space_left].reshape(-1, *input_shape[1:])
+                        if layout is not None:
+                            model.activations_into(z, layer_key, X[mb:mb + space_left])
+                        else:
+                            with torch.no_grad():
+                                model.partial_forward(z, layer_key)
+                            X[mb:mb + space_left] = inst.retained_features()[layer_key].reshape((z.shape[0], -1))
+                    if not transformer.fit_partial_inplace(NB):
+                        break
+                    continue
                 else:
                     X = torch.empty((NB, d), dtype=torch.float32, device=device)
                     for mb in range(0, NB, B):
@@ -285,7 +318,7 @@ def compute_arrays(config, instrumented_model):
     mean_dev = tr.device_attributes()["mean"]
     if affine is None:
         X_global_mean = tr.mean_.reshape((1, sample_dims))
-        Y_comp, Y_mean = X_comp, X_global_mean
+        Y_comp, Y_mean = X_comp, X_global_mean              # device feature order (== the reference's unless `layout`)
     else:
         # lift through the isometry: components = components_y Q^T (svd_flip's sign rule is applied on the lifted
         # rows, as sklearn would on the full activations), mean = mean_y Q^T + offset
@@ -304,20 +337,23 @@ def compute_arrays(config, instrumented_model):
         Z_comp = X_comp
         Z_global_mean = X_global_mean
     else:
-        Z_comp, Z_global_mean = regression(Y_comp, Y_mean, X_stdev, inst, config, affine=affine)
+        Z_comp, Z_global_mean = regression(Y_comp, Y_mean, X_stdev, inst, config, affine=affine, native=layout is not None)
 
     Z_comp /= np.linalg.norm(Z_comp, axis=-1, keepdims=True)
 
     # random projections of the last group's buffer, centred on the global mean (:289-291,312-316)
     random_dirs = get_random_dirs(config.components, int(np.prod(sample_shape)))
     n_rand_samples = min(5000, X.shape[0])
-    dirs_dev = torch.from_numpy(random_dirs).to(device)
+    dirs_dev = torch.from_numpy(to_native(random_dirs)).to(device)
     if affine is not None:                                  # dirs . (x - mean) == (dirs Q) . (y - ybar)
         dirs_dev = _native.linear(dirs_dev, affine.Q.T.float().contiguous())
-    X_stdev_random = _native.project_std(X[:n_rand_samples], dirs_dev, sub=mean_dev).cpu().numpy()
+    sub = mean_dev
+    if large_d:                                             # the engine centred the last group in place by its batch mean
+        sub = mean_dev - tr.last_batch_mean()
+    X_stdev_random = _native.project_std(X[:n_rand_samples], dirs_dev, sub=sub).cpu().numpy()
 
-    X_comp = X_comp.reshape(-1, *sample_shape)
-    X_global_mean = X_global_mean.reshape(sample_shape)
+    X_comp = to_nchw(X_comp).reshape(-1, *sample_shape)
+    X_global_mean = to_nchw(X_global_mean).reshape(sample_shape)
     Z_comp = Z_comp.reshape(-1, *input_shape)
     Z_global_mean = Z_global_mean.reshape(input_shape)
 

@@ -6,7 +6,9 @@ interface (``batch_support``, ``get_param_str``, ``fit``, ``fit_partial``, ``get
 ``singular_values_``, ``explained_variance_``, ``explained_variance_ratio_``, ``n_samples_seen_``) but the
 arithmetic of ``IncrementalPCA.partial_fit`` runs on the device: per-batch statistics (csrc/stats.cu)
 feed the fp64 Gram-form merge chain (csrc/ipca.cu).  Batches may be host ndarrays (copied in, as the
-reference API allows) or CUDA tensors (no copy: the samples never leave HBM).
+reference API allows) or CUDA tensors (no copy: the samples never leave HBM).  For d > 1024 (conv feature
+maps) the d x d Gram is out of reach and the small-side engine (csrc/bigd.cu) takes over behind the same
+interface; its stacked matrix lives in HBM and producers can write batches in place (``batch_buffer``).
 
 The other estimators of the reference (pca / fbpca / ica / spca, estimators.py:18-52,84-204) are not
 batched and appear in no BASELINE config; asking for them raises (SURVEY.md section 2 marks them out of
@@ -35,17 +37,50 @@ class DeviceIncrementalPCA:
         self.n_samples_seen_ = np.int64(0)
 
     # -- device side ---------------------------------------------------------------------------------
-    def _ensure(self, d, device):
+    SMALL_D_MAX = 1024          # above this the d x d Gram engine (csrc/ipca.cu) gives way to the small-side engine (bigd.cu)
+
+    def _ensure(self, d, device, nb=None):
         if self._chain is None:
             if self.n_components > d:
                 raise ValueError(
                     "n_components=%r invalid for n_features=%d, need more rows than columns for "
                     "IncrementalPCA processing" % (self.n_components, d))
-            self._chain = _native.IPCAChain(d, self.n_components, device)
+            if d > self.SMALL_D_MAX:
+                self._chain = _native.BigIPCA(d, self.n_components, nb, device)
+            else:
+                self._chain = _native.IPCAChain(d, self.n_components, device)
         elif self._chain.d != d:
             raise ValueError("Number of input features has changed from %i to %i between calls to partial_fit!"
                              % (self._chain.d, d))
         return self._chain
+
+    @property
+    def is_large_d(self):
+        return isinstance(self._chain, _native.BigIPCA)
+
+    def batch_buffer(self, nb, d, device):
+        """Large-d engine only: the [nb, d] rows of the device-resident stacked matrix that the NEXT partial_fit will
+        consume.  Producers (e.g. the synthesis kernels) write the raw batch there; then ``partial_fit_inplace(nb)``."""
+        if d <= self.SMALL_D_MAX:
+            raise ValueError("batch_buffer is the large-d engine's interface (d > %d)" % self.SMALL_D_MAX)
+        chain = self._ensure(int(d), device, nb=int(nb))
+        if nb > chain.nb_max:                                   # a later batch larger than the first: grow, keep the state
+            big = _native.BigIPCA(chain.d, chain.c, int(nb), chain.dev)
+            big.M[:chain.c].copy_(chain.M[:chain.c])
+            big.state.copy_(chain.state)
+            big.n_seen = chain.n_seen
+            self._chain = chain = big
+        return chain.batch_rows(int(nb))
+
+    def partial_fit_inplace(self, nb):
+        chain = self._chain
+        if int(self.n_samples_seen_) == 0 and self.n_components > nb:
+            raise ValueError(f"n_components={self.n_components} must be less or equal to the batch number of "
+                             f"samples {nb} for the first partial_fit call.")
+        chain.step(int(nb))          # centres the batch rows in place (chain.batch_mean holds the batch mean)
+        self.n_samples_seen_ = np.int64(chain.n_seen)
+        self._host = None
+        return self
 
     def batch_stats(self, X):
         """(n, mean[d], centred Gram[d,d]) of a batch; host arrays are copied to the device first."""
@@ -70,8 +105,19 @@ class DeviceIncrementalPCA:
         self._host = None
 
     def partial_fit(self, X, y=None):
+        d = int(X.shape[1]) if getattr(X, "ndim", 2) == 2 else 0
+        if d > self.SMALL_D_MAX:
+            if isinstance(X, np.ndarray):
+                X = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32))
+            dev = X.device if X.is_cuda else _native.require_cuda(self._device)
+            self.batch_buffer(X.shape[0], d, dev).copy_(X)      # host arrays are copied in, CUDA tensors stay in HBM
+            return self.partial_fit_inplace(X.shape[0])
         self.merge(*self.batch_stats(X))
         return self
+
+    def last_batch_mean(self):
+        """Large-d engine: fp64 [d] mean of the batch the last partial_fit centred in place."""
+        return self._chain.batch_mean
 
     # -- sklearn attribute names (host copies, fetched lazily) ---------------------------------------
     def device_attributes(self):
@@ -119,6 +165,15 @@ class IPCAEstimator:
         try:
             self.transformer.partial_fit(X)
             self.transformer.n_samples_seen_ = np.int64(self.transformer.n_samples_seen_)   # estimators.py:71-72
+            return True
+        except ValueError as e:
+            print("\nIPCA error:", e)
+            return False
+
+    def fit_partial_inplace(self, nb):
+        """fit_partial on the batch already written into ``transformer.batch_buffer(nb, d, device)`` (large-d engine)."""
+        try:
+            self.transformer.partial_fit_inplace(nb)
             return True
         except ValueError as e:
             print("\nIPCA error:", e)

@@ -7,8 +7,10 @@ followed by ``Generator(size, 512, 8)`` gives the reference's random init bit-fo
 BASELINE.json configs use random-init weights).
 
 Only the hot path computes: ``Generator.style`` (PixelNorm + 8 x EqualLinear, model.py:400-409) runs
-the hand-written mapping kernels through the C ABI.  The synthesis blocks are parameter holders in
-this round; calling them raises (SURVEY.md section 8 row a5 is built next).
+the hand-written mapping kernels through the C ABI, and the StyledConv chain conv1, convs.0 .. convs.k runs
+as ONE C-ABI call (csrc/synthesis.cu) driven by ``models.wrappers.StyleGAN2.partial_forward``; the modules
+below hold the parameters in the reference's layout and give the hooks their names.  ToRGB / full image
+synthesis are not on the path and raise.
 """
 from __future__ import annotations
 
@@ -96,8 +98,9 @@ def _make_kernel(k):
 class _NotBuilt(nn.Module):
     def forward(self, *a, **k):
         raise NotImplementedError(
-            f"{self.__class__.__name__}: StyleGAN2 synthesis kernels (SURVEY.md section 8 row a5) are not built in this "
-            "round; only layer='style' (the mapping network) is accelerated. There is no PyTorch/CPU fallback.")
+            f"{self.__class__.__name__} has no stand-alone forward: the StyledConv chain runs as one fused C-ABI call "
+            "(StyleGAN2.partial_forward(x, 'conv1' | 'convs.k')); ToRGB / image synthesis are not on the B200 hot path. "
+            "There is no PyTorch/CPU fallback.")
 
 
 class Blur(_NotBuilt):
@@ -143,10 +146,13 @@ class NoiseInjection(_NotBuilt):
         self.weight = nn.Parameter(torch.zeros(1))
 
 
-class ConstantInput(_NotBuilt):
+class ConstantInput(nn.Module):
     def __init__(self, channel, size=4):
         super().__init__()
         self.input = nn.Parameter(torch.randn(1, channel, size, size))
+
+    def forward(self, input):
+        return self.input.repeat(input.shape[0], 1, 1, 1)      # model.py:300-304
 
 
 class FusedLeakyReLU(_NotBuilt):
@@ -156,7 +162,10 @@ class FusedLeakyReLU(_NotBuilt):
         self.negative_slope, self.scale = negative_slope, scale
 
 
-class StyledConv(_NotBuilt):
+class StyledConv(nn.Module):
+    """model.py:307-341.  The arithmetic of the whole conv1 .. convs.k chain is one fused C-ABI call
+    (``_native.PackedSynthesis``); ``forward(_result=act)`` only hands that result to the forward hooks."""
+
     def __init__(self, in_channel, out_channel, kernel_size, style_dim, upsample=False, blur_kernel=(1, 3, 3, 1),
                  demodulate=True):
         super().__init__()
@@ -164,6 +173,20 @@ class StyledConv(_NotBuilt):
                                     blur_kernel=blur_kernel, demodulate=demodulate)
         self.noise = NoiseInjection()
         self.activate = FusedLeakyReLU(out_channel)
+
+    def forward(self, input=None, style=None, noise=None, _result=None):
+        if _result is None:
+            raise NotImplementedError(
+                "StyledConv runs as part of the fused synthesis chain (StyleGAN2.partial_forward(x, 'convs.k')); a "
+                "stand-alone per-layer call is not built and there is no PyTorch fallback")
+        return _result
+
+    def describe(self, noise_map, res_in):
+        """Layer descriptor for _native.PackedSynthesis (device tensors in PyTorch layout)."""
+        c = self.conv
+        return dict(conv_weight=c.weight[0], mod_weight=c.modulation.weight, mod_bias=c.modulation.bias,
+                    act_bias=self.activate.bias, noise=noise_map.reshape(-1), noise_weight=self.noise.weight,
+                    upsample=c.upsample, res_in=res_in)
 
 
 class ToRGB(_NotBuilt):

@@ -186,6 +186,8 @@ class StyleGAN2(BaseModel):
     def check_numerics(self):
         """Raise if a kernel flagged an out-of-range activation since the weights were packed (synchronises)."""
         self.model.style.packed().check()
+        if getattr(self, "_synth_cache", None) is not None:
+            self._synth_cache[1].check()
 
     def get_max_latents(self):
         return self.model.n_latent
@@ -200,15 +202,72 @@ class StyleGAN2(BaseModel):
                             truncation_latent=self.latent_avg, input_is_w=self.w_primary)
         return 0.5 * (out + 1)
 
+    # ---- synthesis chain conv1, convs.0 .. convs.k (wrappers.py:224-255) ------------------------------------
+    def synthesis_layer_names(self):
+        return ["conv1"] + [f"convs.{i}" for i in range(len(self.model.convs))]
+
+    def _synthesis(self, n_run):
+        """PackedSynthesis covering at least the first ``n_run`` StyledConv layers (re-packed when a parameter or a
+        noise map of those layers changes, or when a deeper layer is asked for)."""
+        mods = [self.model.conv1] + list(self.model.convs)
+        cst = self.model.input.input
+        keys = [(cst._version, cst.data_ptr())]
+        keys += [(m.conv.weight._version, m.conv.weight.data_ptr(), m.conv.modulation.weight._version,
+                  m.conv.modulation.bias._version, m.noise.weight._version, m.activate.bias._version,
+                  self.noise[i].data_ptr(), self.noise[i]._version) for i, m in enumerate(mods[:n_run])]
+        cached = getattr(self, "_synth_cache", None)
+        if cached is None or len(cached[0]) < len(keys) or cached[0][:len(keys)] != keys:
+            layers, res = [], 4
+            for i, m in enumerate(mods[:n_run]):
+                layers.append(m.describe(self.noise[i], res))
+                res = 2 * res if m.conv.upsample else res
+            packed = _native.PackedSynthesis(cst.detach()[0], layers, self.model.style_dim)
+            self._synth_cache = cached = (keys, packed)
+        return cached[1]
+
+    def feature_layout(self, layer_name):
+        """Native (device) feature order of ``activations_into`` for this layer: ('nhwc', (H, W, C)); the reference's
+        flattening is NCHW -- a fixed permutation, applied once to the exported components."""
+        names = self.synthesis_layer_names()
+        if layer_name not in names:
+            return None
+        res, co = self._synthesis(names.index(layer_name) + 1).shapes[names.index(layer_name)]
+        return ("nhwc", (res, res, co))
+
+    def activations_into(self, x, layer_name, out):
+        """Hooked-layer activations of latents x [n,512] (in the current primary space) written as fp32 NHWC rows into
+        ``out`` [n, H*W*C] (may be row-strided): the decomposition driver's producer for conv layers."""
+        names = self.synthesis_layer_names()
+        n_run = names.index(layer_name) + 1
+        w = x if self.w_primary else self.model.style(x)
+        return self._synthesis(n_run).forward(w.reshape(-1, 512), n_run, out=out)
+
     def partial_forward(self, x, layer_name):
         styles = x if isinstance(x, list) else [x]
         if not self.w_primary:
             styles = [self.model.style(s) for s in styles]
         if "style" in layer_name:
             return
-        raise NotImplementedError(
-            f"StyleGAN2.partial_forward to layer '{layer_name}': the synthesis blocks (SURVEY.md section 8 row a5) "
-            "are not built in this round; there is no PyTorch fallback")
+        if layer_name == "input":
+            self.model.input(styles[0])
+            return
+        names = self.synthesis_layer_names()
+        if layer_name not in names:
+            raise NotImplementedError(
+                f"StyleGAN2.partial_forward to layer '{layer_name}': only style, input, conv1 and convs.k are on the "
+                "B200 hot path (ToRGB / image synthesis: SURVEY.md section 8f); there is no PyTorch fallback")
+        if len(styles) != 1:
+            raise NotImplementedError("style mixing (several latents per sample) is not built for the fused synthesis chain")
+        mods = [self.model.conv1] + list(self.model.convs)
+        target = names.index(layer_name)
+        w = styles[0].reshape(-1, 512)
+        # the chain runs fused; layers before the target that carry hooks get their own (shorter) run
+        hooked = [i for i in range(target) if len(mods[i]._forward_hooks)]
+        for i in hooked + [target]:
+            syn = self._synthesis(target + 1)
+            res, co = syn.shapes[i]
+            act = syn.forward(w, i + 1).view(-1, res, res, co).permute(0, 3, 1, 2)    # NCHW view of NHWC storage
+            mods[i](_result=act)
 
     def set_noise_seed(self, seed):
         # same generator stream as the reference (torch.manual_seed(seed); torch.randn per noise map),

@@ -127,7 +127,8 @@ int gsb_ipca_export(const void *d_state, int d, int c, int64_t n_seen,
                     gsb_stream_t stream);
 
 /* Stand-alone symmetric eigensolver used by the chain (test hook): top-c eigenpairs of the fp64
- * symmetric matrix d_a[d,d] (destroyed); d_evals[c] descending, d_evecs[c,d] rows, sign-normalised. */
+ * symmetric matrix d_a[d,d] (destroyed); d_evals[c] descending, d_evecs[c,d] rows, sign-normalised.
+ * d <= 1024: cluster / shared-memory tridiagonalisation; 1024 < d <= 4096: L2-resident variant. */
 int gsb_sym_eig_top(double *d_a, int d, int c, double *d_evals, double *d_evecs,
                     void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
 
@@ -158,6 +159,63 @@ int gsb_linreg_accumulate(void *d_state, int c, int latent_dim, const float *d_a
 size_t gsb_linreg_workspace_bytes(int64_t n, int c);
 int gsb_linreg_solve(void *d_state, int c, int latent_dim, int64_t n_total, double *d_M_t,
                      double *d_z_mean, gsb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * StyleGAN2 synthesis up to a hooked StyledConv (layer = conv1 | convs.k; BASELINE config 5 family)
+ *   replaces  models/wrappers.py:224-255 (StyleGAN2.partial_forward past 'style') over
+ *             models/stylegan2/stylegan2-pytorch/model.py:181-277 (ModulatedConv2d), :280-291 (NoiseInjection),
+ *             :294-304 (ConstantInput), :307-341 (StyledConv), op/fused_act.py:86-92, op/upfirdn2d.py:144-198 (Blur)
+ *   for ONE global latent per sample (every layer's style is the same w, wrappers.py:202-205).
+ * Layers are described in execution order: layers[0] = conv1 (on the 4x4 constant), layers[k+1] = convs.k.
+ * All pointers in the descriptors are device pointers to the module's fp32 parameters in PyTorch layout.
+ * gsb_synthesis_pack folds the conv scale, splits the shared weights for the tcgen05 GEMM, pre-computes
+ * sum_tap w^2 for the demodulation and noise_weight*noise; gsb_synthesis_forward runs layers[0..n_run) on
+ * w[n, style_dim] and writes the last layer's activation as fp32 **NHWC** rows (index (y*res + x)*cout + co;
+ * the reference's NCHW flattening is a fixed permutation of it) at d_out + b*ld_out.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct gsb_styled_conv {
+    const float *conv_weight;  /* [cout, cin, 3, 3]   ModulatedConv2d.weight[0]            model.py:222-224 */
+    const float *mod_weight;   /* [cin, style_dim]    ModulatedConv2d.modulation.weight    model.py:226     */
+    const float *mod_bias;     /* [cin]               ModulatedConv2d.modulation.bias (init 1)              */
+    const float *act_bias;     /* [cout]              FusedLeakyReLU.bias                  fused_act.py:78  */
+    const float *noise;        /* [res_out, res_out]  the fixed noise map of this layer    wrappers.py:261-267 */
+    const float *noise_weight; /* [1]                 NoiseInjection.weight                model.py:284     */
+    int cin, cout;             /* cin % 128 == 0, cout % 256 == 0 */
+    int upsample;              /* 1: stride-2 transposed conv + blur (res_out = 2 res_in)  model.py:248-259 */
+    int res_in;                /* input resolution (4 for conv1) */
+} gsb_styled_conv;
+
+size_t gsb_synthesis_packed_bytes(const gsb_styled_conv *layers, int n_layers, int style_dim);
+int gsb_synthesis_pack(const gsb_styled_conv *layers, int n_layers, int style_dim, const float *d_const_input /* [cin0,4,4] */,
+                       void *d_packed, size_t packed_bytes, gsb_stream_t stream);
+size_t gsb_synthesis_workspace_bytes(const gsb_styled_conv *layers, int n_run, int64_t n);
+int gsb_synthesis_forward(const void *d_packed, const gsb_styled_conv *layers, int n_layers, int n_run, int style_dim,
+                          const float *d_w, int64_t n, float *d_out, int64_t ld_out, void *d_workspace,
+                          size_t workspace_bytes, gsb_stream_t stream);
+/* synchronises; *h_flags bit0 = an operand left fp16's range since the pack (results invalid) */
+int gsb_synthesis_status(const void *d_packed, const gsb_styled_conv *layers, int n_layers, int style_dim, unsigned *h_flags);
+
+/* ------------------------------------------------------------------------------------------------
+ * Incremental PCA, large-d engine (conv feature maps: d up to ~10^6, where the d x d Gram of gsb_ipca_* is out of reach)
+ *   replaces  estimators.py:55-81 -> sklearn IncrementalPCA.partial_fit (_incremental_pca.py:254-380) through the
+ *   small side of sklearn's stacked matrix  M = [S*Vt ; X - mean_b ; mean-correction row]  (c + n_b + 1 rows of d).
+ * The caller owns M: fp32 [gsb_bigd_rows(c, nb_max), d] row-major.  Rows [0, c) hold singular_values_*components_
+ * (engine state); before every step the caller writes the raw batch into rows [c, c + nb) -- the producer kernels
+ * write there directly -- and gsb_bigd_chain_step centres it IN PLACE, forms T = M M^T (fp32 products, fp64 sums),
+ * takes its top-c eigenpairs in fp64 (direct solver on the first step, warm-started block Lanczos afterwards) and
+ * replaces rows [0, c) by U^T M with sklearn's svd_flip signs.  d_batch_mean (optional, [d]) receives the batch mean.
+ * Feature order is whatever the producer uses (PCA is equivariant under a fixed permutation of the features).
+ * ---------------------------------------------------------------------------------------------- */
+int gsb_bigd_rows(int c, int nb_max);
+size_t gsb_bigd_state_bytes(int64_t d, int c);
+size_t gsb_bigd_workspace_bytes(int64_t d, int c, int nb_max);
+int gsb_bigd_reset(void *d_state, float *d_M, int64_t d, int c, int nb_max, gsb_stream_t stream);
+int gsb_bigd_chain_step(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+                        double *d_batch_mean, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
+/* components_ [c,d] as fp32 (any pointer may be NULL); the small vectors and mean_/var_ [d] as fp64 */
+int gsb_bigd_export(const void *d_state, const float *d_M, int64_t d, int c, int64_t n_seen, float *d_components,
+                    double *d_singular_values, double *d_mean, double *d_var, double *d_explained_variance,
+                    double *d_explained_variance_ratio, gsb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -301,7 +301,8 @@ class _GlobalSeeds:
 
 
 def compute_path(sample, activate, latent_dims: int, feat_dims: int, n: int, B: int, c: int,
-                 samples_are_latents: bool, seed=None, ipca: str = "svd", use_w: bool = False, return_aux=False):
+                 samples_are_latents: bool, seed=None, ipca: str = "svd", use_w: bool = False, return_aux=False,
+                 regress: bool = True):
     """Restated decomposition.compute (:150-341) for estimator='ipca'.
         sample(seed, B)   -> one model.sample_latent(B) call (latents [B, latent_dims], float32)
         activate(latents) -> the hooked layer's activations flattened to [B, feat_dims]
@@ -335,6 +336,8 @@ def compute_path(sample, activate, latent_dims: int, feat_dims: int, n: int, B: 
 
     if samples_are_latents:                                          # :297-299
         Z_comp, Z_mean = X_comp, X_global_mean
+    elif not regress:                                                # (test shortcut: PCA half only, lat_* left as placeholders)
+        Z_comp, Z_mean = np.ones((c, latent_dims)), np.zeros((1, latent_dims))
     else:                                                            # :301-305 -> linreg_lstsq :77-139
         Z_comp, Z_mean = linreg(sample, activate, latent_dims, X_comp, X_global_mean, X_stdev, n, B)
     Z_comp = Z_comp / np.linalg.norm(Z_comp, axis=-1, keepdims=True)  # :308
@@ -471,3 +474,183 @@ def compare_npz(ours: dict, ref: dict) -> dict:
         "lat_mean_rel": rel("lat_mean"), "lat_stdev_rel": rel("lat_stdev"),
         "random_stdevs_rel": rel("random_stdevs"),
     }
+
+
+# --------------------------------------------------------------------------------------------
+# StyleGAN2 synthesis up to a hooked StyledConv  (wrappers.py:194-259; stylegan2-pytorch/model.py:181-341)
+# --------------------------------------------------------------------------------------------
+STYLEGAN2_CHANNELS = {4: 512, 8: 512, 16: 512, 32: 512, 64: 512, 128: 256, 256: 128, 512: 64, 1024: 32}
+
+
+def synthesis_layer_names(upto: str):
+    """Hookable StyledConv layers in execution order up to ``upto`` ('conv1', 'convs.0', ...) (wrappers.py:224-255)."""
+    names = ["conv1"]
+    if upto != "conv1":
+        k = int(upto.split(".")[1])
+        names += [f"convs.{i}" for i in range(k + 1)]
+    return names
+
+
+def synthesis_random_init(seed: int = 1234, size: int = 1024, upto: str = "convs.4"):
+    """Random-init synthesis tensors of ``Generator(size, 512, 8)`` under ``torch.manual_seed(seed)``, replaying the
+    reference's parameter creation order (model.py:384-469): style (8 x randn(512,512)), input (randn(1,512,4,4) :298),
+    conv1 [ModulatedConv2d weight randn(1,co,ci,3,3) :222-224, modulation EqualLinear randn(ci,512) bias 1 :226],
+    to_rgb1 [weight randn(1,3,512,1,1), modulation], the ``noises`` buffers (:434-437), then per resolution
+    convs[2j] (upsample), convs[2j+1], to_rgbs[j].  NoiseInjection.weight = 0 (:284), FusedLeakyReLU.bias = 0."""
+    import math
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    for _ in range(8):
+        rn(512, 512)                                                  # mapping network (mapping_random_init)
+    log_size = int(math.log(size, 2))
+    ch = STYLEGAN2_CHANNELS
+    const = rn(1, ch[4], 4, 4).numpy()[0]
+
+    def styled(ci, co, upsample, res_out):
+        w = rn(1, co, ci, 3, 3).numpy()[0]
+        mw = rn(ci, 512).numpy()
+        return dict(weight=w, mod_weight=mw, mod_bias=np.ones(ci, np.float32), noise_weight=np.float32(0.0),
+                    act_bias=np.zeros(co, np.float32), upsample=upsample, res_out=res_out)
+
+    def to_rgb(ci):
+        rn(1, 3, ci, 1, 1); rn(ci, 512)
+
+    layers = {"conv1": styled(ch[4], ch[4], False, 4)}
+    to_rgb(ch[4])
+    for layer_idx in range((log_size - 2) * 2 + 1):
+        res = (layer_idx + 5) // 2
+        rn(1, 1, 2 ** res, 2 ** res)
+    wanted = synthesis_layer_names(upto)
+    in_ch = ch[4]
+    for i in range(3, log_size + 1):
+        out_ch = ch[2 ** i]
+        layers[f"convs.{2 * (i - 3)}"] = styled(in_ch, out_ch, True, 2 ** i)
+        layers[f"convs.{2 * (i - 3) + 1}"] = styled(out_ch, out_ch, False, 2 ** i)
+        to_rgb(out_ch)
+        in_ch = out_ch
+        if wanted[-1] in layers:
+            break
+    return dict(const=const, layers={k: layers[k] for k in wanted})
+
+
+def fixed_noise(seed: int = 0, size: int = 1024):
+    """wrappers.py:261-267 set_noise_seed: torch.manual_seed(seed); randn(1,1,4,4); two maps per resolution 8..size."""
+    import math
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    noise = [torch.randn(1, 1, 4, 4, generator=g).numpy()[0, 0]]
+    for i in range(3, int(math.log(size, 2)) + 1):
+        for _ in range(2):
+            noise.append(torch.randn(1, 1, 2 ** i, 2 ** i, generator=g).numpy()[0, 0])
+    return noise
+
+
+BLUR_K2D = (np.outer([1, 3, 3, 1], [1, 3, 3, 1]).astype(np.float32) / np.float32(64.0)) * np.float32(4.0)   # model.py:47-57,81-84
+
+
+def styled_conv_forward(x, w, L, noise):
+    """One StyledConv exactly as the reference computes it on the CPU: per-sample modulated + demodulated weights,
+    grouped conv / stride-2 transposed conv + upfirdn2d blur (model.py:232-277), NoiseInjection (:287-291),
+    FusedLeakyReLU CPU fallback (fused_act.py:86-90).  x [B,ci,H,W], w [B,512] float32 -> [B,co,H',W']."""
+    import math
+    import torch
+    import torch.nn.functional as F
+    x = torch.from_numpy(np.ascontiguousarray(x, np.float32))
+    w = torch.from_numpy(np.ascontiguousarray(w, np.float32))
+    weight = torch.from_numpy(L["weight"])[None]                         # [1,co,ci,3,3]
+    co, ci = weight.shape[1], weight.shape[2]
+    B, _, H, W = x.shape
+    mscale = 1 / math.sqrt(512)                                           # EqualLinear.scale, lr_mul = 1 (:143)
+    style = F.linear(w, torch.from_numpy(L["mod_weight"]) * mscale, bias=torch.from_numpy(L["mod_bias"]) * 1.0)
+    style = style.view(B, 1, ci, 1, 1)
+    weight = (1 / math.sqrt(ci * 9)) * weight * style                    # :236
+    demod = torch.rsqrt(weight.pow(2).sum([2, 3, 4]) + 1e-8)             # :239
+    weight = weight * demod.view(B, co, 1, 1, 1)
+    weight = weight.view(B * co, ci, 3, 3)
+    if L["upsample"]:
+        inp = x.reshape(1, B * ci, H, W)
+        wt = weight.view(B, co, ci, 3, 3).transpose(1, 2).reshape(B * ci, co, 3, 3)
+        out = F.conv_transpose2d(inp, wt, padding=0, stride=2, groups=B)   # :255
+        out = out.view(B, co, 2 * H + 1, 2 * W + 1)
+        # Blur(pad=(1,1), kernel*4) -> upfirdn2d_native: pad, true convolution (flipped kernel) (upfirdn2d.py:157-198)
+        out = F.pad(out, [1, 1, 1, 1]).reshape(B * co, 1, 2 * H + 3, 2 * W + 3)
+        kflip = torch.flip(torch.from_numpy(BLUR_K2D), [0, 1]).view(1, 1, 4, 4)
+        out = F.conv2d(out, kflip).view(B, co, 2 * H, 2 * W)
+    else:
+        inp = x.reshape(1, B * ci, H, W)
+        out = F.conv2d(inp, weight, padding=1, groups=B).view(B, co, H, W)   # :272
+    out = out + torch.tensor(float(L["noise_weight"])) * torch.from_numpy(np.asarray(noise, np.float32))[None, None]
+    out = (2 ** 0.5) * F.leaky_relu(out + torch.from_numpy(L["act_bias"]).view(1, -1, 1, 1), negative_slope=0.2)
+    return out.numpy()
+
+
+def styled_conv_taps(x_nhwc, w, L, noise):
+    """The same StyledConv in the form the CUDA path uses (numpy, float64 accumulation): scale the INPUT channels by
+    the style, one dense contraction per 3x3 tap with the shared weights (Y[b,p,tap,co] = sum_ci W[co,ci,tap] xs[b,p,ci]),
+    gather the nine tap planes (stride-1) or scatter them on the 2x grid and blur (upsample), multiply by
+    demod[b,co] = rsqrt(sum_ci s^2 sum_k (scale W)^2 + 1e-8), add noise and bias, leaky-ReLU * sqrt2.
+    x_nhwc [B,H,W,ci] -> [B,H',W',co].  Algebraically identical to styled_conv_forward."""
+    x = np.asarray(x_nhwc, np.float64)
+    B, H, W, ci = x.shape
+    Wt = L["weight"].astype(np.float64) / np.sqrt(ci * 9.0)              # [co,ci,3,3]
+    co = Wt.shape[0]
+    s = np.asarray(w, np.float64) @ (L["mod_weight"].astype(np.float64) / np.sqrt(512.0)).T + L["mod_bias"]
+    demod = 1.0 / np.sqrt((s * s) @ (Wt ** 2).sum(axis=(2, 3)).T + 1e-8)     # [B,co]
+    xs = x * s[:, None, None, :]
+    Y = np.einsum("bhwi,oikl->bhwklo", xs, Wt)                           # [B,H,W,ky,kx,co]
+    if L["upsample"]:
+        T = np.zeros((B, 2 * H + 1, 2 * W + 1, co))
+        for ky in range(3):
+            for kx in range(3):
+                T[:, ky:ky + 2 * H:2, kx:kx + 2 * W:2, :] += Y[:, :, :, ky, kx, :]   # out_t[2y+ky, 2x+kx]
+        Tp = np.pad(T, [(0, 0), (1, 1), (1, 1), (0, 0)])
+        out = np.zeros((B, 2 * H, 2 * W, co))
+        kb = BLUR_K2D.astype(np.float64)
+        for i in range(4):
+            for j in range(4):
+                out += kb[i, j] * Tp[:, i:i + 2 * H, j:j + 2 * W, :]
+    else:
+        Yp = np.pad(Y, [(0, 0), (1, 1), (1, 1), (0, 0), (0, 0), (0, 0)])
+        out = np.zeros((B, H, W, co))
+        for ky in range(3):
+            for kx in range(3):
+                out += Yp[:, ky:ky + H, kx:kx + W, ky, kx, :]           # in[y+ky-1, x+kx-1]
+    out = out * demod[:, None, None, :]
+    out = out + float(L["noise_weight"]) * np.asarray(noise, np.float64)[None, :, :, None] + L["act_bias"].astype(np.float64)
+    out = np.sqrt(2.0) * np.where(out >= 0, out, 0.2 * out)
+    return out
+
+
+def synthesis_forward(w, params, noises, upto: str, form: str = "reference"):
+    """wrappers.py:224-255 for one global latent: input -> conv1(noise[0]) -> convs.0(noise[1]) -> convs.1(noise[2]) ...
+    (every layer's style is the same w: latent[:, i] of the repeated [B,n_latent,512] tensor :202-205).
+    Returns the hooked layer's activation [B,co,H,W] float32."""
+    B = w.shape[0]
+    x = np.repeat(params["const"][None], B, axis=0)                      # ConstantInput (:300-304)
+    if form == "taps":
+        x = x.transpose(0, 2, 3, 1)
+    for idx, name in enumerate(synthesis_layer_names(upto)):
+        L = params["layers"][name]
+        x = styled_conv_forward(x, w, L, noises[idx]) if form == "reference" else styled_conv_taps(x, w, L, noises[idx])
+    return x if form == "reference" else x.transpose(0, 3, 1, 2)
+
+
+def compute_stylegan2_layer(weights, biases, params, layer: str, n: int, B: int, c: int, size: int = 1024, seed=None,
+                            return_aux: bool = False, regress: bool = True):
+    """model=StyleGAN2, layer=conv1|convs.k, Z space (decomposition.py:150-341): activations = synthesis(mapping(z))
+    flattened NCHW; IncrementalPCA in its sklearn (stacked-SVD) form; regression back to z."""
+    noises = fixed_noise(0, size)
+    normals = lambda s, B_: standard_normal_f32(s, 512 * B_).reshape(B_, 512)
+
+    def activate(z):
+        out = []
+        for i in range(0, z.shape[0], 64):
+            out.append(synthesis_forward(mapping_forward(z[i:i + 64], weights, biases), params, noises, layer))
+        a = np.concatenate(out, axis=0)
+        return a.reshape(a.shape[0], -1)
+
+    L = params["layers"][layer]
+    d = L["weight"].shape[0] * L["res_out"] ** 2
+    return compute_path(normals, activate, 512, d, n, B, c, False, seed=seed, ipca="svd", return_aux=return_aux,
+                        regress=regress)

@@ -50,12 +50,87 @@ def _import_reference():
     return wrappers, stylegan2, Config, decomposition, estimators
 
 
+def perturb_synthesis(model, names):
+    """Deterministic non-zero NoiseInjection weights / FusedLeakyReLU biases (both are 0 at random init, which would
+    leave the noise and bias paths of the kernels untested)."""
+    for i, name in enumerate(names):
+        mod = dict(model.named_modules())[name]
+        with torch.no_grad():
+            mod.noise.weight.fill_(0.1 * (i + 1))
+            mod.activate.bias.copy_(0.1 * torch.sin(torch.arange(mod.activate.bias.shape[0], dtype=torch.float32) + i))
+
+
+def synthesis_golden(wrappers, stylegan2, Config, decomposition, orc, dev):
+    """G7/G8: StyleGAN2 synthesis up to a hooked StyledConv (BASELINE config 5 family)."""
+    class RandInitStyleGAN2(wrappers.StyleGAN2):
+        def load_model(self):
+            torch.manual_seed(1234)
+            self.model = stylegan2.Generator(self.resolution, 512, 8).to(self.device)
+            self.latent_avg = torch.zeros(512, device=self.device)
+
+    names = ["conv1"] + [f"convs.{i}" for i in range(5)]
+    # ---- G7: known answers of partial_forward, with perturbed noise weights / biases ---------------------------
+    m = RandInitStyleGAN2(dev, "ffhq")
+    sd = {k: v.clone() for k, v in m.model.state_dict().items()}
+    perturb_synthesis(m.model, names)
+    m.use_z()
+    z = m.sample_latent(4, seed=21)
+    ka = dict(z=z.numpy())
+    with torch.no_grad():
+        ka["w"] = m.model.style(z).numpy()
+    for layer, keep in (("conv1", 4), ("convs.0", 4), ("convs.1", 4), ("convs.2", 2), ("convs.3", 1), ("convs.4", 1)):
+        inst = wrappers.get_instrumented_model("StyleGAN2", "ffhq", layer, dev, model=m, use_w=False)
+        with torch.no_grad():
+            m.partial_forward(z[:keep], layer)
+        act = inst.retained_features()[layer].numpy()
+        key = layer.replace(".", "_")
+        if act[0].size <= 131072:
+            ka[f"act_{key}"] = act
+        else:                                                # 2 MB per sample: keep a strided subsample + moments
+            ka[f"act_{key}_sub"] = act[:, ::4, ::2, ::2].copy()
+        ka[f"sum_{key}"] = np.array([act.astype(np.float64).sum(), (act.astype(np.float64) ** 2).sum()])
+        inst.close()
+    ka["const_sum"] = np.array(float(sd["input.input"].double().sum()))
+    for nme in names:
+        ka[f"wsum_{nme.replace('.', '_')}"] = np.array([float(sd[f"{nme}.conv.weight"].double().sum()),
+                                                        float(sd[f"{nme}.conv.modulation.weight"].double().sum())])
+    ka["noise_heads"] = np.stack([n.numpy().reshape(-1)[:4] for n in m.noise[:6]])
+    np.savez_compressed(OUT / "synthesis_known_answers.npz", **ka)
+
+    # ---- G8: layer=convs.1 (d = 32768) and convs.2 (d = 131072), Z space, pure random init -----------------------
+    for layer, n, b, c in (("convs.1", 4_000, 500, 8), ("convs.2", 4_000, 250, 6)):
+        m2 = RandInitStyleGAN2(dev, "ffhq")
+        inst = wrappers.get_instrumented_model("StyleGAN2", "ffhq", layer, dev, model=m2, use_w=False)
+        cfg = Config(model="StyleGAN2", layer=layer, output_class="ffhq", estimator="ipca", use_w=False,
+                     n=n, batch_size=b, components=c)
+        with tempfile.TemporaryDirectory() as tmp:
+            path = decomposition.get_or_compute(cfg, inst, force_recompute=True,
+                                                submit_config=SimpleNamespace(run_dir=tmp, run_dir_root=tmp))
+            with np.load(path) as data:
+                out = {k: data[k].copy() for k in data.files}
+            name = path.name
+        np.savez_compressed(OUT / f"c5s_stylegan2_ffhq_{layer.replace('.', '')}_z_n{n}_b{b}_c{c}.npz",
+                            dump_name=np.array(name), **out)
+        inst.close()
+
+    # oracle vs reference
+    p = orc.synthesis_random_init(1234, 1024, "convs.4")
+    assert np.array_equal(p["const"], sd["input.input"].numpy()[0])
+    for nme in names:
+        assert np.array_equal(p["layers"][nme]["weight"], sd[f"{nme}.conv.weight"].numpy()[0]), nme
+        assert np.array_equal(p["layers"][nme]["mod_weight"], sd[f"{nme}.conv.modulation.weight"].numpy()), nme
+    print("synthesis init: oracle == reference")
+
+
 def main():
     wrappers, stylegan2, Config, decomposition, estimators = _import_reference()
     sys.path.insert(0, str(REPO))
     from oracle import ganspace_oracle as orc
     OUT.mkdir(parents=True, exist_ok=True)
     dev = torch.device("cpu")
+    if "--only-synthesis" in sys.argv:
+        synthesis_golden(wrappers, stylegan2, Config, decomposition, orc, dev)
+        return
 
     class RandInitStyleGAN2(wrappers.StyleGAN2):
         def load_model(self):                      # replaces checkpoint download (wrappers.py:153-165)
@@ -167,6 +242,8 @@ def main():
                         bias_head=gz.bias[:8].detach().numpy(), u_head=gz.weight_u[:8].numpy(), v_head=gz.weight_v[:8].numpy(),
                         emb_head=bm.model.embeddings.weight[:4, :6].detach().numpy(),
                         trunc_seed5=biggan.truncated_noise_sample(batch_size=4, seed=5))
+
+    synthesis_golden(wrappers, stylegan2, Config, decomposition, orc, dev)
 
     # ---- report oracle-vs-reference (also asserted by tests/test_oracle_golden.py) -----------------
     ws, bs = orc.mapping_random_init(1234)

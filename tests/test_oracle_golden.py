@@ -77,3 +77,60 @@ def test_biggan_genz_compute_restatement_vs_reference(oracle, golden):
         assert cmp[k] < 1e-4, (k, cmp)
     for k in out:
         assert out[k].shape == g[k].shape and out[k].dtype == g[k].dtype, k
+
+
+# ---- StyleGAN2 synthesis -------------------------------------------------------------
+def _perturbed_params(oracle, upto):
+    p = oracle.synthesis_random_init(1234, 1024, upto)
+    for i, name in enumerate(oracle.synthesis_layer_names(upto)):
+        p["layers"][name]["noise_weight"] = np.float32(0.1 * (i + 1))
+        p["layers"][name]["act_bias"] = (0.1 * np.sin(np.arange(512, dtype=np.float32) + i)).astype(np.float32)
+    return p
+
+
+def test_synthesis_init_and_known_answers(oracle, golden, mapping_weights):
+    """Oracle restatement of the StyledConv chain vs the unmodified reference's partial_forward outputs."""
+    g = golden("synthesis_known_answers.npz")
+    p = _perturbed_params(oracle, "convs.4")
+    assert np.isclose(float(p["const"].astype(np.float64).sum()), float(g["const_sum"]), rtol=1e-12)
+    for name in oracle.synthesis_layer_names("convs.4"):
+        L = p["layers"][name]
+        sums = [float(L["weight"].astype(np.float64).sum()), float(L["mod_weight"].astype(np.float64).sum())]
+        assert np.allclose(sums, g[f"wsum_{name.replace('.', '_')}"], rtol=1e-12), name
+    noises = oracle.fixed_noise(0, 1024)
+    assert np.array_equal(np.stack([n.reshape(-1)[:4] for n in noises[:6]]), g["noise_heads"])
+    w = oracle.mapping_forward(g["z"], *mapping_weights)
+    assert np.abs(w - g["w"]).max() < 1e-6
+    for layer, keep in (("conv1", 4), ("convs.1", 4), ("convs.2", 2)):
+        ref = g[f"act_{layer.replace('.', '_')}"]
+        act = oracle.synthesis_forward(g["w"][:keep], p, noises, layer)
+        assert act.shape == ref.shape
+        assert np.abs(act - ref).max() <= 2e-5 * np.abs(ref).max(), layer
+    act = oracle.synthesis_forward(g["w"][:1], p, noises, "convs.4")
+    assert np.abs(act[:, ::4, ::2, ::2] - g["act_convs_4_sub"]).max() <= 2e-5 * np.abs(act).max()
+    sums = np.array([act.astype(np.float64).sum(), (act.astype(np.float64) ** 2).sum()])
+    assert np.allclose(sums, g["sum_convs_4"], rtol=1e-5)
+
+
+def test_synthesis_tap_form_equals_reference_form(oracle):
+    """The contraction-per-tap form the CUDA kernels implement == the reference's per-sample grouped conv."""
+    p = _perturbed_params(oracle, "convs.2")
+    noises = oracle.fixed_noise(0, 1024)
+    w = np.random.RandomState(3).standard_normal((3, 512)).astype(np.float32)
+    a = oracle.synthesis_forward(w, p, noises, "convs.2")
+    b = oracle.synthesis_forward(w, p, noises, "convs.2", form="taps")
+    assert np.abs(a - b).max() < 5e-5 * np.abs(a).max()
+
+
+def test_conv_layer_pca_restatement_vs_reference(oracle, golden, mapping_weights):
+    """PCA half of compute() on layer convs.1 (d = 32768): oracle vs the unmodified reference's .npz."""
+    g = golden("c5s_stylegan2_ffhq_convs1_z_n4000_b500_c8.npz")
+    p = oracle.synthesis_random_init(1234, 1024, "convs.1")
+    out = oracle.compute_stylegan2_layer(*mapping_weights, p, "convs.1", 4000, 500, 8, regress=False)
+    a = out["act_comp"].reshape(8, -1).astype(np.float64)
+    b = g["act_comp"].reshape(8, -1).astype(np.float64)
+    assert np.sum(a * b, axis=1).min() > 0.99999
+    assert np.abs(out["var_ratio"] - g["var_ratio"]).max() < 1e-6
+    assert np.allclose(out["act_stdev"], g["act_stdev"], rtol=1e-4)
+    assert np.allclose(out["act_mean"].reshape(-1), g["act_mean"].reshape(-1), atol=1e-5)
+    assert np.allclose(out["random_stdevs"], g["random_stdevs"], rtol=1e-4)
