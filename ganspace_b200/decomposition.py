@@ -161,7 +161,8 @@ def linreg_lstsq(comp_np, mean_np, stdev_np, inst, config, affine=None, native=F
 
 def regression(comp, mean, stdev, inst, config, affine=None, native=False):
     M = np.dot(comp, comp.T)
-    if not np.allclose(M, np.identity(M.shape[0])):
+    # fp32 components (large-d engine) are orthonormal to ~1e-6, the reference's float64 ones to 1e-15
+    if not np.allclose(M, np.identity(M.shape[0]), atol=1e-8 if comp.dtype == np.float64 else 5e-6):
         det = np.linalg.det(M)
         print(f"WARNING: Computed basis is not orthonormal (determinant={det})")
     return linreg_lstsq(comp, mean, stdev, inst, config, affine=affine, native=native)
