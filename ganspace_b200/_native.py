@@ -575,7 +575,8 @@ class BigIPCA:
             _check(lib.gsb_bigd_chain_step(_ptr(self.state), _ptr(self.M), self.d, self.c, self.nb_max, self.n_seen, int(nb),
                                            _ptr(self.batch_mean), _ptr(self.ws), self.ws.numel(), _stream()),
                    "gsb_bigd_chain_step")
-        lanczos = self.n_seen > 0 and self.c % 16 == 0 and self.c <= 128 and 3 * self.c <= self.rows // 2 + self.rows // 8
+        lanczos = (os.environ.get("GANSPACE_B200_BIGD_CHAIN") == "lanczos" and self.n_seen > 0 and self.c % 16 == 0
+                   and self.c <= 128 and 3 * self.c <= self.rows // 2 + self.rows // 8)
         instrument.count(6 + (37 if lanczos else 5))
         self.n_seen += int(nb)
         self.last_nb = int(nb)

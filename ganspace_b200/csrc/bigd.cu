@@ -10,14 +10,17 @@
 // (synthesis.cu) writes the batch rows in place -- and the SVD goes through the SMALL side:
 //        T = M M^T  (n_s x n_s, n_s = c + n_b + 1 ~ 2100; fp32 products summed in fp32 over 8192-long chunks of d,
 //                    chunks accumulated in fp64)
-//        T = U diag(lambda) U^T  (top c; fp64: direct solver on the first step, afterwards the warm-started block
-//                    Lanczos of ipca.cu -- the previous components are the first c coordinates of the small side,
-//                    and M^T maps its Krylov space onto the feature-side one, so the accuracy argument is the same)
+//        T = U diag(lambda) U^T  (top c; fp64 direct solver: L2-resident Householder tridiagonalisation, bisection,
+//                    inverse iteration (ipca.cu).  Optional: the warm-started block Lanczos of ipca.cu -- the previous
+//                    components are the first c coordinates of the small side and M^T maps its Krylov space onto the
+//                    feature-side one)
 //        S_new = sqrt(lambda),   (S * Vt)_new = U^T M      (one skinny GEMM over M; rows 0..c-1 of M for the next step)
 // followed by sklearn's svd_flip sign rule on the rows and the Chan mean / variance merge per feature
 // (extmath._incremental_mean_and_var).  Nothing of size d x d or n_b x d ever leaves the device.
 #include "ipca_internal.cuh"
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace gsb {
 
@@ -36,6 +39,19 @@ static BigState big_state(void *p, int64_t d, int c) {
     return s;
 }
 
+// Measured on config 5 (convs.4, d = 524288, N = 200k, c = 80): the warm-started Lanczos step agrees with the direct
+// solver to cos 0.99994 on the trailing components (conv feature maps have much smaller eigen-gaps than W space, where
+// it reaches 0.999999997) and saves only ~16 ms of a ~90 ms step, so the exact direct solve is the default here;
+// GANSPACE_B200_BIGD_CHAIN=lanczos opts in.
+static bool bigd_use_lanczos() {
+    static int v = -1;
+    if (v == -1) {
+        const char *env = getenv("GANSPACE_B200_BIGD_CHAIN");
+        v = (env && strcmp(env, "lanczos") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 struct BigWs {
     Workspace ew;          // ew.A doubles as T
     void *lan;
@@ -52,7 +68,7 @@ static BigWs big_ws(void *base, int64_t d, int c, int nb_max) {
     auto take = [&](size_t bytes) { char *q = p + off; off += align_up(bytes, 256); return q; };
     const size_t eb = carve(nullptr, np, c).bytes;
     w.ew = carve(take(eb), np, c);
-    w.lanczos = lanczos_applicable(np, c);
+    w.lanczos = bigd_use_lanczos() && lanczos_applicable(np, c);
     w.lan = w.lanczos ? take(carve_lanczos(nullptr, np, c).bytes) : nullptr;
     w.mean_b = (double *)take((size_t)d * 8);
     w.E = (double *)take((size_t)c * np * 8);

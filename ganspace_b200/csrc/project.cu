@@ -18,16 +18,18 @@ __device__ __forceinline__ void project_tile(const float *__restrict__ x, int64_
                                              const float *__restrict__ dirs, int c,
                                              const double *__restrict__ sub64,
                                              const float *__restrict__ sub32, int64_t r0, int k0,
-                                             float (&acc)[8], float (*Xs)[PJ_K + 1], float (*Cs)[PJ_K + 1]) {
+                                             float (&acc)[8], float (*Xs)[PJ_K + 1], float (*Cs)[PJ_K + 1],
+                                             int i_begin = 0, int i_end = -1) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
     for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-    for (int i0 = 0; i0 < d; i0 += PJ_K) {
+    if (i_end < 0 || i_end > d) i_end = d;
+    for (int i0 = i_begin; i0 < i_end; i0 += PJ_K) {
         for (int rr = ty; rr < PJ_ROWS; rr += 8) {
             int64_t r = r0 + rr;
             int i = i0 + tx;
             float v = 0.f;
-            if (r < n && i < d) {
+            if (r < n && i < i_end) {
                 v = x[r * ld + i];
                 if (SUBMODE == 1) v = (float)((double)v - sub64[i]);
                 if (SUBMODE == 2) v = v - sub32[i];
@@ -36,7 +38,7 @@ __device__ __forceinline__ void project_tile(const float *__restrict__ x, int64_
         }
         for (int kk = ty; kk < PJ_COMPS; kk += 8) {
             int k = k0 + kk, i = i0 + tx;
-            Cs[kk][tx] = (k < c && i < d) ? dirs[(int64_t)k * d + i] : 0.f;
+            Cs[kk][tx] = (k < c && i < i_end) ? dirs[(int64_t)k * d + i] : 0.f;
         }
         __syncthreads();
 #pragma unroll 8
@@ -91,14 +93,20 @@ linreg_coords_kernel(const float *__restrict__ act, int64_t n, int d, const floa
     const int k0 = blockIdx.y * PJ_COMPS;
     const int64_t r0 = (int64_t)blockIdx.x * PJ_ROWS;
     float acc[8];
-    project_tile<2>(act, n, d, d, comp, c, nullptr, mean, r0, k0, acc, Xs, Cs);
+    // gridDim.z > 1 (conv feature maps, d ~ 10^5..10^6): the feature axis is split over CTAs, partial coordinates are
+    // added with fp32 atomics into the zeroed A (the division by stdev distributes over the partial sums)
+    const int slab = (int)(((int64_t)d + gridDim.z - 1) / gridDim.z + PJ_K - 1) / PJ_K * PJ_K;
+    const int i_begin = blockIdx.z * slab;
+    project_tile<2>(act, n, d, d, comp, c, nullptr, mean, r0, k0, acc, Xs, Cs, i_begin, i_begin + slab);
     const int k = k0 + tx;
     if (k >= c) return;
     const float sd = stdev[k];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         int64_t row = r0 + ty + 8 * r;
-        if (row < n) A[row * c + k] = acc[r] / sd;
+        if (row >= n) continue;
+        if (gridDim.z == 1) A[row * c + k] = acc[r] / sd;
+        else atomicAdd(&A[row * c + k], acc[r] / sd);
     }
 }
 
@@ -248,7 +256,13 @@ extern "C" int gsb_linreg_accumulate(void *d_state, int c, int latent_dim, const
     cudaStream_t st = (cudaStream_t)stream;
     gsb::LinregView v = gsb::linreg_view(d_state, c, latent_dim);
     float *A = reinterpret_cast<float *>(d_workspace);
-    dim3 g1((unsigned)((n + gsb::PJ_ROWS - 1) / gsb::PJ_ROWS), (c + gsb::PJ_COMPS - 1) / gsb::PJ_COMPS);
+    int splits = 1;                                           // few row tiles and a long feature axis: split d
+    {
+        const int64_t tiles = ((n + gsb::PJ_ROWS - 1) / gsb::PJ_ROWS) * ((c + gsb::PJ_COMPS - 1) / gsb::PJ_COMPS);
+        while (splits < 64 && tiles * splits < 8 * gsb::num_sms() && d / (2 * splits) >= 4096) splits *= 2;
+    }
+    if (splits > 1) GSB_CHECK_CUDA(cudaMemsetAsync(A, 0, (size_t)n * c * sizeof(float), st));
+    dim3 g1((unsigned)((n + gsb::PJ_ROWS - 1) / gsb::PJ_ROWS), (c + gsb::PJ_COMPS - 1) / gsb::PJ_COMPS, splits);
     gsb::linreg_coords_kernel<<<g1, 256, 0, st>>>(d_act, n, d, d_comp, c, d_mean, d_stdev, A);
     GSB_CHECK_LAUNCH();
     dim3 g2((c + latent_dim + gsb::NE_T - 1) / gsb::NE_T, (c + gsb::NE_T - 1) / gsb::NE_T,

@@ -176,15 +176,34 @@ def compute(config, dump_name, instrumented_model):
     rank, world, live = _dist()
     if rank == 0:
         os.makedirs(dump_name.parent, exist_ok=True)
-        np.savez_compressed(dump_name, **arrays)
+        # same 8-array .npz; conv feature maps (act_comp = 168 MB at convs.4) are stored uncompressed: single-core
+        # deflate of incompressible float32 data would cost more than the whole device computation
+        big = sum(a.nbytes for a in arrays.values()) > (64 << 20)
+        (np.savez if big else np.savez_compressed)(dump_name, **arrays)
     if live:
         import torch.distributed as dist
         dist.barrier()
 
 
+def _phase_timer():
+    """GANSPACE_B200_TIMING=1: print wall-clock per phase (synchronising); otherwise a no-op."""
+    if os.environ.get("GANSPACE_B200_TIMING") != "1":
+        return lambda label: None
+    import time
+    state = {"t": time.perf_counter()}
+
+    def tick(label):
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        print(f"[timing] {label}: {now - state['t']:.3f} s", flush=True)
+        state["t"] = now
+    return tick
+
+
 def compute_arrays(config, instrumented_model):
     """Everything of compute() up to (not including) the file write; returns the 8 float32 arrays."""
     global B
+    tick = _phase_timer()
 
     torch.manual_seed(0)
     np.random.seed(0)
@@ -314,6 +333,7 @@ def compute_arrays(config, instrumented_model):
         dist.all_reduce(slots)                         # the run's single exchange of PCA statistics
         _plan.replay(pl, slots, d, lambda nb, m, g: tr.merge(nb, m.contiguous(), g.contiguous()))
 
+    tick("sampling + activations + IPCA chain")
     X_comp, X_stdev, X_var_ratio = transformer.get_components()
     X_comp = np.array(X_comp, copy=True)
     mean_dev = tr.device_attributes()["mean"]
@@ -340,12 +360,19 @@ def compute_arrays(config, instrumented_model):
     else:
         Z_comp, Z_global_mean = regression(Y_comp, Y_mean, X_stdev, inst, config, affine=affine, native=layout is not None)
 
+    tick("export + regression")
     Z_comp /= np.linalg.norm(Z_comp, axis=-1, keepdims=True)
 
     # random projections of the last group's buffer, centred on the global mean (:289-291,312-316)
-    random_dirs = get_random_dirs(config.components, int(np.prod(sample_shape)))
     n_rand_samples = min(5000, X.shape[0])
-    dirs_dev = torch.from_numpy(to_native(random_dirs)).to(device)
+    if layout is not None and config.components * sample_dims >= (1 << 22):
+        # get_random_dirs' stream (RandomState(2).normal) drawn by the device generator: 42M normals at convs.4
+        g = _native.legacy_normal([SEED_RANDOM_DIRS], config.components * sample_dims, device).view(config.components, -1)
+        g = g / torch.linalg.vector_norm(g.double(), dim=1, keepdim=True).float()
+        dirs_dev = g.view(config.components, lc, lh, lw).permute(0, 2, 3, 1).reshape(config.components, -1).contiguous()
+    else:
+        random_dirs = get_random_dirs(config.components, int(np.prod(sample_shape)))
+        dirs_dev = torch.from_numpy(to_native(random_dirs)).to(device)
     if affine is not None:                                  # dirs . (x - mean) == (dirs Q) . (y - ybar)
         dirs_dev = _native.linear(dirs_dev, affine.Q.T.float().contiguous())
     sub = mean_dev
@@ -366,6 +393,7 @@ def compute_arrays(config, instrumented_model):
 
     if hasattr(model, "check_numerics"):
         model.check_numerics()
+    tick("random directions + layout")
     arrays = {
         "act_comp": X_comp.astype(np.float32),
         "act_mean": X_global_mean.astype(np.float32),

@@ -202,7 +202,7 @@ int gsb_synthesis_status(const void *d_packed, const gsb_styled_conv *layers, in
  * The caller owns M: fp32 [gsb_bigd_rows(c, nb_max), d] row-major.  Rows [0, c) hold singular_values_*components_
  * (engine state); before every step the caller writes the raw batch into rows [c, c + nb) -- the producer kernels
  * write there directly -- and gsb_bigd_chain_step centres it IN PLACE, forms T = M M^T (fp32 products, fp64 sums),
- * takes its top-c eigenpairs in fp64 (direct solver on the first step, warm-started block Lanczos afterwards) and
+ * takes its top-c eigenpairs in fp64 (direct solver; GANSPACE_B200_BIGD_CHAIN=lanczos: warm-started block Lanczos) and
  * replaces rows [0, c) by U^T M with sklearn's svd_flip signs.  d_batch_mean (optional, [d]) receives the batch mean.
  * Feature order is whatever the producer uses (PCA is equivariant under a fixed permutation of the features).
  * ---------------------------------------------------------------------------------------------- */
