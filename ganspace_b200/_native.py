@@ -55,6 +55,10 @@ SIGNATURES = {
     "gsb_bigd_reset": (_I, [_P, _P, _L, _I, _I, _P]),
     "gsb_bigd_chain_step": (_I, [_P, _P, _L, _I, _I, _L, _I, _P, _P, _Z, _P]),
     "gsb_bigd_export": (_I, [_P, _P, _L, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
+    "gsb_bigd_gram_matrix": (_P, [_P, _L, _I, _I]),
+    "gsb_bigd_step_gram": (_I, [_P, _P, _L, _I, _I, _L, _I, _P, _P, _Z, _P]),
+    "gsb_bigd_step_solve": (_I, [_P, _P, _L, _I, _I, _L, _I, _P, _P, _Z, _P]),
+    "gsb_bigd_step_commit": (_I, [_P, _P, _L, _I, _I, _L, _I, _P, _P, _Z, _P]),
 }
 
 
@@ -544,13 +548,43 @@ class PackedSynthesis:
             raise NativeError("synthesis: an operand exceeded fp16 range in the tensor-core path; results are invalid")
 
 
+def pick_global_signs(rowmax_all: torch.Tensor) -> torch.Tensor:
+    """svd_flip across feature shards: rowmax_all [W, c, 2] = per shard (max |.|, its signed value); the sign of the
+    global maximum wins, ties go to the lowest shard (= lowest feature index, np.argmax's first-occurrence rule)."""
+    idx = torch.argmax(rowmax_all[:, :, 0], dim=0)                      # first maximal shard per row
+    val = rowmax_all[idx, torch.arange(rowmax_all.shape[1], device=rowmax_all.device), 1]
+    return torch.where(val < 0, -torch.ones_like(val), torch.ones_like(val)).contiguous()
+
+
+def exchange_rows(stage: torch.Tensor, out: torch.Tensor, world: int, group=None):
+    """Row-parallel -> feature-sharded exchange of one IPCA batch.  ``stage`` [q, d]: the q rows
+    this rank produced, all d features; ``out`` [world*q, d/world]: every rank's rows for THIS rank's feature block,
+    in rank (= sample) order.  One all-to-all; the send side is packed by a strided copy."""
+    import torch.distributed as dist
+    q, d = stage.shape
+    dl = d // world
+    assert d % world == 0 and out.shape == (world * q, dl) and out.is_contiguous()
+    send = stage.view(q, world, dl).permute(1, 0, 2).contiguous()       # [world, q, dl]: block s goes to rank s
+    dist.all_to_all_single(out.view(world, q, dl), send, group=group)
+    return out
+
+
 class BigIPCA:
     """Large-d IncrementalPCA engine (csrc/bigd.cu): the stacked matrix M = [S*Vt; batch; correction] lives in HBM,
-    producers write the batch rows in place (``batch_rows``), ``step`` runs one partial_fit."""
+    producers write the batch rows in place (``batch_rows``), ``step`` runs one partial_fit.
 
-    def __init__(self, d: int, c: int, nb_max: int, device):
+    ``shard=(rank, world)``: feature-sharded over a torch.distributed job -- this object holds the column block
+    d/world of M; ``step`` all-reduces the small-side Gram (fp64, (c+nb+1)^2) and agrees on the svd_flip signs."""
+
+    def __init__(self, d: int, c: int, nb_max: int, device, shard=None):
         lib = load()
         self.dev = require_cuda(device)
+        self.shard = shard if (shard is not None and shard[1] > 1) else None
+        self.d_full = int(d)
+        if self.shard is not None:
+            if d % (16 * self.shard[1]) != 0:
+                raise NativeError(f"feature sharding needs d % (16*world) == 0 (d={d}, world={self.shard[1]})")
+            d = d // self.shard[1]
         self.d, self.c, self.nb_max = int(d), int(c), int(nb_max)
         ws_bytes = lib.gsb_bigd_workspace_bytes(self.d, self.c, self.nb_max)
         if ws_bytes == 0:
@@ -564,24 +598,42 @@ class BigIPCA:
         self.last_nb = 0
         with torch.cuda.device(self.dev):
             _check(lib.gsb_bigd_reset(_ptr(self.state), _ptr(self.M), self.d, self.c, self.nb_max, _stream()), "gsb_bigd_reset")
+        if self.shard is not None:
+            t_ptr = lib.gsb_bigd_gram_matrix(_ptr(self.ws), self.d, self.c, self.nb_max)
+            off = int(t_ptr) - self.ws.data_ptr()
+            self._T = self.ws[off:off + self.rows * self.rows * 8].view(torch.float64)
+            self._rowmax = torch.empty((self.c, 2), dtype=torch.float32, device=self.dev)
 
     def batch_rows(self, nb: int) -> torch.Tensor:
         assert 1 <= nb <= self.nb_max
         return self.M[self.c:self.c + nb]
 
+    def _args(self, nb):
+        return (_ptr(self.state), _ptr(self.M), self.d, self.c, self.nb_max, self.n_seen, int(nb))
+
     def step(self, nb: int):
         lib = load()
+        tail = (_ptr(self.ws), self.ws.numel(), _stream())
         with torch.cuda.device(self.dev), instrument.section("chain"):
-            _check(lib.gsb_bigd_chain_step(_ptr(self.state), _ptr(self.M), self.d, self.c, self.nb_max, self.n_seen, int(nb),
-                                           _ptr(self.batch_mean), _ptr(self.ws), self.ws.numel(), _stream()),
-                   "gsb_bigd_chain_step")
+            if self.shard is None:
+                _check(lib.gsb_bigd_chain_step(*self._args(nb), _ptr(self.batch_mean), *tail), "gsb_bigd_chain_step")
+            else:
+                import torch.distributed as dist
+                _check(lib.gsb_bigd_step_gram(*self._args(nb), _ptr(self.batch_mean), *tail), "gsb_bigd_step_gram")
+                dist.all_reduce(self._T)                                   # small-side Gram summed over the feature shards
+                _check(lib.gsb_bigd_step_solve(*self._args(nb), _ptr(self._rowmax), *tail), "gsb_bigd_step_solve")
+                allmax = torch.empty((self.shard[1] * self.c, 2), dtype=torch.float32, device=self.dev)
+                dist.all_gather_into_tensor(allmax, self._rowmax)          # concatenated along dim 0 in rank order
+                signs = pick_global_signs(allmax.view(self.shard[1], self.c, 2))
+                _check(lib.gsb_bigd_step_commit(*self._args(nb), _ptr(signs), *tail), "gsb_bigd_step_commit")
         lanczos = (os.environ.get("GANSPACE_B200_BIGD_CHAIN") == "lanczos" and self.n_seen > 0 and self.c % 16 == 0
                    and self.c <= 128 and 3 * self.c <= self.rows // 2 + self.rows // 8)
-        instrument.count(6 + (37 if lanczos else 5))
+        instrument.count(7 + (37 if lanczos else 5))
         self.n_seen += int(nb)
         self.last_nb = int(nb)
 
     def export(self):
+        """sklearn's attributes; under feature sharding every rank returns the full-width arrays (one all-gather)."""
         lib = load()
         f64 = dict(dtype=torch.float64, device=self.dev)
         out = {
@@ -596,4 +648,28 @@ class BigIPCA:
                                        _ptr(out["explained_variance"]), _ptr(out["explained_variance_ratio"]), _stream()),
                    "gsb_bigd_export")
         instrument.count(3)
+        if self.shard is not None:
+            import torch.distributed as dist
+            W = self.shard[1]
+            comp = torch.empty((W * self.c, self.d), dtype=torch.float32, device=self.dev)
+            dist.all_gather_into_tensor(comp, out["components"])
+            out["components"] = comp.view(W, self.c, self.d).permute(1, 0, 2).reshape(self.c, W * self.d).contiguous()
+            for k in ("mean", "var"):
+                full = torch.empty(W * self.d, **f64)
+                dist.all_gather_into_tensor(full, out[k])
+                out[k] = full
+            # explained_variance_ratio_ = S^2 / sum(var * n) over ALL features (_incremental_pca.py:366-367)
+            out["explained_variance_ratio"] = out["singular_values"] ** 2 / (out["var"].sum() * self.n_seen)
         return out
+
+    def gathered(self, local: torch.Tensor) -> torch.Tensor:
+        """[n, d_local] column blocks of every rank -> [n, d_full] (identity without sharding)."""
+        if self.shard is None:
+            return local
+        import torch.distributed as dist
+        W = self.shard[1]
+        local = local.contiguous()
+        n, dl = local.shape
+        full = torch.empty((W * n, dl), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(full, local)
+        return full.view(W, n, dl).permute(1, 0, 2).reshape(n, W * dl).contiguous()

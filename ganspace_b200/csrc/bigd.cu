@@ -56,7 +56,7 @@ struct BigWs {
     Workspace ew;          // ew.A doubles as T
     void *lan;
     double *mean_b, *E, *U, *lam;
-    float *Dnew;
+    float *Dnew, *rowmax;
     size_t bytes;
     bool lanczos;
 };
@@ -75,6 +75,7 @@ static BigWs big_ws(void *base, int64_t d, int c, int nb_max) {
     w.U = (double *)take((size_t)c * np * 8);
     w.lam = (double *)take((size_t)c * 8);
     w.Dnew = (float *)take((size_t)c * d * 4);
+    w.rowmax = (float *)take((size_t)2 * c * 4);
     w.bytes = off;
     return w;
 }
@@ -268,10 +269,9 @@ bigd_project_kernel(const double *__restrict__ U, int ldu, const float *__restri
 }
 
 // svd_flip (u_based_decision=False): the entry of largest magnitude of every row becomes positive (first index on
-// ties); writes the signed rows into M[0..c) and S = sqrt(lambda).  One CTA per row.
+// ties).  Phase 1: rowmax[t] = (max |.|, its signed value) over this device's features.  One CTA per row.
 __global__ void __launch_bounds__(1024)
-bigd_sign_rows_kernel(const float *__restrict__ Dnew, int64_t d, const double *__restrict__ lam, float *__restrict__ M,
-                      double *__restrict__ S, double *__restrict__ hdr, double n_tot) {
+bigd_rowmax_kernel(const float *__restrict__ Dnew, int64_t d, float *__restrict__ rowmax) {
     __shared__ float s_best[32];
     __shared__ float s_val[32];
     __shared__ long long s_idx[32];
@@ -297,10 +297,18 @@ bigd_sign_rows_kernel(const float *__restrict__ Dnew, int64_t d, const double *_
             const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ob > best || (ob == best && oi < bi)) { best = ob; bval = ov; bi = oi; }
         }
-        if (lane == 0) s_val[0] = (bval < 0.f) ? -1.f : 1.f;
+        if (lane == 0) { rowmax[2 * t] = best; rowmax[2 * t + 1] = bval; }
     }
-    __syncthreads();
-    const float sgn = s_val[0];
+}
+// Phase 2: rows [0, c) of M <- sign * Dnew, S = sqrt(lambda).  `signs` == nullptr: the sign of this device's own
+// row maximum (single GPU); otherwise the signs agreed across the feature shards.
+__global__ void __launch_bounds__(1024)
+bigd_commit_kernel(const float *__restrict__ Dnew, int64_t d, const double *__restrict__ lam, const float *__restrict__ rowmax,
+                   const float *__restrict__ signs, float *__restrict__ M, double *__restrict__ S, double *__restrict__ hdr,
+                   double n_tot) {
+    const int t = blockIdx.x, tid = threadIdx.x;
+    const float sgn = signs ? ((signs[t] < 0.f) ? -1.f : 1.f) : ((rowmax[2 * t + 1] < 0.f) ? -1.f : 1.f);
+    const float *row = Dnew + (size_t)t * d;
     float *dst = M + (size_t)t * d;
     for (int64_t i = tid; i < d; i += 1024) dst[i] = sgn * row[i];
     if (tid == 0) {
@@ -366,45 +374,86 @@ extern "C" int gsb_bigd_reset(void *d_state, float *d_M, int64_t d, int c, int n
     return GSB_OK;
 }
 
-extern "C" int gsb_bigd_chain_step(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
-                                   double *d_batch_mean, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
-    using namespace gsb;
-    GSB_CHECK_ARG(d_state && d_M && d_workspace, "bigd_chain_step: null pointer");
+namespace gsb {
+struct StepCtx { BigWs w; BigState s; int np, n_rows; cudaStream_t st; };
+static int step_ctx(StepCtx &x, void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb, void *d_workspace,
+                    size_t workspace_bytes, gsb_stream_t stream) {
+    GSB_CHECK_ARG(d_state && d_M && d_workspace, "bigd step: null pointer");
     if (int r = bigd_check(d, c, nb_max)) return r;
-    GSB_CHECK_ARG(nb >= 1 && nb <= nb_max && n_seen >= 0, "bigd_chain_step: bad batch size %d (nb_max=%d)", nb, nb_max);
-    GSB_CHECK_ARG(n_seen > 0 || c <= nb, "bigd_chain_step: n_components=%d > first batch size %d", c, nb);
-    BigWs w = big_ws(d_workspace, d, c, nb_max);
-    if (workspace_bytes < w.bytes) { set_error("bigd_chain_step: workspace too small (%zu < %zu)", workspace_bytes, w.bytes); return GSB_ERR_WORKSPACE; }
-    cudaStream_t st = (cudaStream_t)stream;
-    BigState s = big_state(d_state, d, c);
-    const int np = bigd_rows(c, nb_max);
-    const int n_rows = c + nb + 1;
+    GSB_CHECK_ARG(nb >= 1 && nb <= nb_max && n_seen >= 0, "bigd step: bad batch size %d (nb_max=%d)", nb, nb_max);
+    GSB_CHECK_ARG(n_seen > 0 || c <= nb, "bigd step: n_components=%d > first batch size %d", c, nb);
+    x.w = big_ws(d_workspace, d, c, nb_max);
+    if (workspace_bytes < x.w.bytes) { set_error("bigd step: workspace too small (%zu < %zu)", workspace_bytes, x.w.bytes); return GSB_ERR_WORKSPACE; }
+    x.s = big_state(d_state, d, c);
+    x.np = bigd_rows(c, nb_max);
+    x.n_rows = c + nb + 1;
+    x.st = (cudaStream_t)stream;
+    return GSB_OK;
+}
+}  // namespace gsb
 
-    bigd_center_kernel<<<(unsigned)((d + 255) / 256), 256, 0, st>>>(d_M, d, c, nb, np, (double)n_seen, s.mean, s.unnorm, w.mean_b);
-    GSB_CHECK_LAUNCH();
-    if (d_batch_mean) GSB_CHECK_CUDA(cudaMemcpyAsync(d_batch_mean, w.mean_b, (size_t)d * sizeof(double), cudaMemcpyDeviceToDevice, st));
+extern "C" void *gsb_bigd_gram_matrix(void *d_workspace, int64_t d, int c, int nb_max) {
+    if (!d_workspace || gsb::bigd_check(d, c, nb_max)) return nullptr;
+    return gsb::big_ws(d_workspace, d, c, nb_max).ew.A;
+}
 
-    double *T = w.ew.A;
-    GSB_CHECK_CUDA(cudaMemsetAsync(T, 0, (size_t)np * np * sizeof(double), st));
-    {
-        const int nt = (n_rows + GB - 1) / GB;
-        dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)((d + BD_KCHUNK - 1) / BD_KCHUNK));
-        bigd_gram_kernel<<<grid, 256, 0, st>>>(d_M, n_rows, d, BD_KCHUNK, T, np);
-        GSB_CHECK_LAUNCH();
-    }
-    if (n_seen > 0 && w.lanczos) {
-        bigd_unit_rows_kernel<<<(c * np + 255) / 256, 256, 0, st>>>(w.E, c, np);
-        GSB_CHECK_LAUNCH();
-        LanczosWs lw = carve_lanczos(w.lan, np, c);
-        if (int r = eig_top_lanczos(lw, T, w.E, np, c, w.lam, w.U, st)) return r;
-    } else {
-        if (int r = eig_top(w.ew, np, c, w.lam, w.U, st)) return r;
-    }
-    bigd_project_kernel<<<(unsigned)((d + PJ_COLS - 1) / PJ_COLS), 256, 0, st>>>(w.U, np, d_M, n_rows, d, c, w.Dnew);
+// phase 1: centre the batch rows, update mean / variance, T = M M^T over THIS device's features
+extern "C" int gsb_bigd_step_gram(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+                                  double *d_batch_mean, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
+    using namespace gsb;
+    StepCtx x;
+    if (int r = step_ctx(x, d_state, d_M, d, c, nb_max, n_seen, nb, d_workspace, workspace_bytes, stream)) return r;
+    bigd_center_kernel<<<(unsigned)((d + 255) / 256), 256, 0, x.st>>>(d_M, d, c, nb, x.np, (double)n_seen, x.s.mean, x.s.unnorm, x.w.mean_b);
     GSB_CHECK_LAUNCH();
-    bigd_sign_rows_kernel<<<c, 1024, 0, st>>>(w.Dnew, d, w.lam, d_M, s.S, s.hdr, (double)(n_seen + nb));
+    if (d_batch_mean) GSB_CHECK_CUDA(cudaMemcpyAsync(d_batch_mean, x.w.mean_b, (size_t)d * sizeof(double), cudaMemcpyDeviceToDevice, x.st));
+    double *T = x.w.ew.A;
+    GSB_CHECK_CUDA(cudaMemsetAsync(T, 0, (size_t)x.np * x.np * sizeof(double), x.st));
+    const int nt = (x.n_rows + GB - 1) / GB;
+    dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)((d + BD_KCHUNK - 1) / BD_KCHUNK));
+    bigd_gram_kernel<<<grid, 256, 0, x.st>>>(d_M, x.n_rows, d, BD_KCHUNK, T, x.np);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
+}
+
+// phase 2: top-c eigenpairs of T (summed over the feature shards by the caller), Dnew = U^T M, per-row maxima
+extern "C" int gsb_bigd_step_solve(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+                                   float *d_rowmax, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
+    using namespace gsb;
+    StepCtx x;
+    if (int r = step_ctx(x, d_state, d_M, d, c, nb_max, n_seen, nb, d_workspace, workspace_bytes, stream)) return r;
+    double *T = x.w.ew.A;
+    if (n_seen > 0 && x.w.lanczos) {
+        bigd_unit_rows_kernel<<<(c * x.np + 255) / 256, 256, 0, x.st>>>(x.w.E, c, x.np);
+        GSB_CHECK_LAUNCH();
+        LanczosWs lw = carve_lanczos(x.w.lan, x.np, c);
+        if (int r = eig_top_lanczos(lw, T, x.w.E, x.np, c, x.w.lam, x.w.U, x.st)) return r;
+    } else {
+        if (int r = eig_top(x.w.ew, x.np, c, x.w.lam, x.w.U, x.st)) return r;
+    }
+    bigd_project_kernel<<<(unsigned)((d + PJ_COLS - 1) / PJ_COLS), 256, 0, x.st>>>(x.w.U, x.np, d_M, x.n_rows, d, c, x.w.Dnew);
+    GSB_CHECK_LAUNCH();
+    bigd_rowmax_kernel<<<c, 1024, 0, x.st>>>(x.w.Dnew, d, x.w.rowmax);
+    GSB_CHECK_LAUNCH();
+    if (d_rowmax) GSB_CHECK_CUDA(cudaMemcpyAsync(d_rowmax, x.w.rowmax, (size_t)2 * c * sizeof(float), cudaMemcpyDeviceToDevice, x.st));
+    return GSB_OK;
+}
+
+// phase 3: commit  S*Vt <- sign * Dnew  (d_signs [c], or NULL = this device's own row maxima), S, sample count
+extern "C" int gsb_bigd_step_commit(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+                                    const float *d_signs, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
+    using namespace gsb;
+    StepCtx x;
+    if (int r = step_ctx(x, d_state, d_M, d, c, nb_max, n_seen, nb, d_workspace, workspace_bytes, stream)) return r;
+    bigd_commit_kernel<<<c, 1024, 0, x.st>>>(x.w.Dnew, d, x.w.lam, x.w.rowmax, d_signs, d_M, x.s.S, x.s.hdr, (double)(n_seen + nb));
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+extern "C" int gsb_bigd_chain_step(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+                                   double *d_batch_mean, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
+    if (int r = gsb_bigd_step_gram(d_state, d_M, d, c, nb_max, n_seen, nb, d_batch_mean, d_workspace, workspace_bytes, stream)) return r;
+    if (int r = gsb_bigd_step_solve(d_state, d_M, d, c, nb_max, n_seen, nb, nullptr, d_workspace, workspace_bytes, stream)) return r;
+    return gsb_bigd_step_commit(d_state, d_M, d, c, nb_max, n_seen, nb, nullptr, d_workspace, workspace_bytes, stream);
 }
 
 extern "C" int gsb_bigd_export(const void *d_state, const float *d_M, int64_t d, int c, int64_t n_seen, float *d_components,

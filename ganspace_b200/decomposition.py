@@ -253,8 +253,12 @@ def compute_arrays(config, instrumented_model):
     large_d = affine is None and not samples_are_latents and sample_dims > transformer.transformer.SMALL_D_MAX
     layout = model.feature_layout(layer_key) if (large_d and hasattr(model, "feature_layout")) else None
     if large_d and live:
-        raise NotImplementedError("large-d layers under torch.distributed need the feature-sharded chain "
-                                  "(SURVEY.md section 8e); run them on one GPU in this round")
+        # row-parallel generation + feature-sharded chain: rank r synthesises rows
+        # [r NB/W, (r+1) NB/W) of every group, one all-to-all hands rank r the feature block r of all NB rows, the
+        # small-side Gram is all-reduced, every rank solves the same small eigenproblem and updates its block.
+        if layout is None:
+            raise NotImplementedError("feature-sharded large-d runs need a model with activations_into / feature_layout")
+        transformer.transformer.enable_feature_sharding(rank, world)
     if layout is not None:
         lh, lw, lc = layout[1]
         to_nchw = lambda A: np.ascontiguousarray(A.reshape(A.shape[0], lh, lw, lc).transpose(0, 3, 1, 2)).reshape(A.shape[0], -1)
@@ -277,11 +281,14 @@ def compute_arrays(config, instrumented_model):
     K = pl.K
     d = affine.rank if affine is not None else sample_dims
     groups_per_chunk = max(1, int(LATENT_CHUNK_BYTES // max(1, NB * input_dims * 4)))
-    slots = torch.zeros((K, _plan.slot_width(d)), dtype=torch.float64, device=device) if live else None
+    slots = torch.zeros((K, _plan.slot_width(d)), dtype=torch.float64, device=device) if (live and not large_d) else None
     X = None
     tr = transformer.transformer
     for c0 in range(0, K, groups_per_chunk):
-        mine = _plan.groups_to_process(pl, rank, world, c0, min(c0 + groups_per_chunk, K))
+        if large_d:                              # every rank takes part in every group (its row range)
+            mine = list(range(c0, min(c0 + groups_per_chunk, K)))
+        else:
+            mine = _plan.groups_to_process(pl, rank, world, c0, min(c0 + groups_per_chunk, K))
         runs = _plan.contiguous_runs(mine)
         # every sample_latent call this rank needs for the chunk, generated by ONE launch (one CTA per seed)
         needed, offsets = _plan.batch_slots(pl, runs)
@@ -298,15 +305,18 @@ def compute_arrays(config, instrumented_model):
                     X = affine.coords(rows)
                 elif large_d:
                     X = tr.batch_buffer(NB, d, device)              # rows of the engine's stacked matrix, in HBM
+                    lo, hi = (rank * (NB // world), (rank + 1) * (NB // world)) if live else (0, NB)   # this rank's rows
                     for mb in range(0, NB, B):
-                        space_left = min(B, NB - mb)
-                        z = rows[mb:mb + space_left].reshape(-1, *input_shape[1:])
+                        a, b_ = max(mb, lo), min(mb + min(B, NB - mb), hi)
+                        if a >= b_:
+                            continue
+                        z = rows[a:b_].reshape(-1, *input_shape[1:])
                         if layout is not None:
-                            model.activations_into(z, layer_key, X[mb:mb + space_left])
+                            model.activations_into(z, layer_key, X[a - lo:b_ - lo])
                         else:
                             with torch.no_grad():
                                 model.partial_forward(z, layer_key)
-                            X[mb:mb + space_left] = inst.retained_features()[layer_key].reshape((z.shape[0], -1))
+                            X[a - lo:b_ - lo] = inst.retained_features()[layer_key].reshape((z.shape[0], -1))
                     if not transformer.fit_partial_inplace(NB):
                         break
                     continue
@@ -328,7 +338,7 @@ def compute_arrays(config, instrumented_model):
                     break
         ensure_rows(lat.shape[0])
         del lat    # X (a view of the last group when samples_are_latents) keeps its storage alive
-    if live:
+    if live and not large_d:
         import torch.distributed as dist
         dist.all_reduce(slots)                         # the run's single exchange of PCA statistics
         _plan.replay(pl, slots, d, lambda nb, m, g: tr.merge(nb, m.contiguous(), g.contiguous()))
@@ -364,7 +374,7 @@ def compute_arrays(config, instrumented_model):
     Z_comp /= np.linalg.norm(Z_comp, axis=-1, keepdims=True)
 
     # random projections of the last group's buffer, centred on the global mean (:289-291,312-316)
-    n_rand_samples = min(5000, X.shape[0])
+    n_rand_samples = min(5000, NB if large_d else X.shape[0])
     if layout is not None and config.components * sample_dims >= (1 << 22):
         # get_random_dirs' stream (RandomState(2).normal) drawn by the device generator: 42M normals at convs.4
         g = _native.legacy_normal([SEED_RANDOM_DIRS], config.components * sample_dims, device).view(config.components, -1)
@@ -378,6 +388,7 @@ def compute_arrays(config, instrumented_model):
     sub = mean_dev
     if large_d:                                             # the engine centred the last group in place by its batch mean
         sub = mean_dev - tr.last_batch_mean()
+        X = tr.last_batch_rows(n_rand_samples)              # (feature shards gathered when distributed)
     X_stdev_random = _native.project_std(X[:n_rand_samples], dirs_dev, sub=sub).cpu().numpy()
 
     X_comp = to_nchw(X_comp).reshape(-1, *sample_shape)

@@ -34,7 +34,16 @@ class DeviceIncrementalPCA:
         self._device = device
         self._chain = None
         self._host = None            # cached export
+        self._shard = None           # (rank, world): feature-sharded large-d engine
+        self._stage = None
         self.n_samples_seen_ = np.int64(0)
+
+    def enable_feature_sharding(self, rank, world):
+        """Large-d engine over a torch.distributed job: every rank keeps d/world features of the stacked matrix and
+        produces nb/world rows of each batch; ``partial_fit_inplace`` exchanges them with one all-to-all."""
+        if self._chain is not None:
+            raise RuntimeError("enable_feature_sharding must precede the first partial_fit")
+        self._shard = (int(rank), int(world)) if world > 1 else None
 
     # -- device side ---------------------------------------------------------------------------------
     SMALL_D_MAX = 1024          # above this the d x d Gram engine (csrc/ipca.cu) gives way to the small-side engine (bigd.cu)
@@ -46,7 +55,7 @@ class DeviceIncrementalPCA:
                     "n_components=%r invalid for n_features=%d, need more rows than columns for "
                     "IncrementalPCA processing" % (self.n_components, d))
             if d > self.SMALL_D_MAX:
-                self._chain = _native.BigIPCA(d, self.n_components, nb, device)
+                self._chain = _native.BigIPCA(d, self.n_components, nb, device, shard=self._shard)
             else:
                 self._chain = _native.IPCAChain(d, self.n_components, device)
         elif self._chain.d != d:
@@ -64,6 +73,15 @@ class DeviceIncrementalPCA:
         if d <= self.SMALL_D_MAX:
             raise ValueError("batch_buffer is the large-d engine's interface (d > %d)" % self.SMALL_D_MAX)
         chain = self._ensure(int(d), device, nb=int(nb))
+        if self._shard is not None:
+            # sharded: the caller fills a staging buffer with ITS rows [rank*q, (rank+1)*q) of the batch, all d features
+            world = self._shard[1]
+            if nb % world != 0 or nb > chain.nb_max:
+                raise ValueError(f"feature-sharded IPCA needs equal batches divisible by the world size (nb={nb}, world={world})")
+            q = nb // world
+            if self._stage is None or self._stage.shape != (q, int(d)):
+                self._stage = torch.empty((q, int(d)), dtype=torch.float32, device=chain.dev)
+            return self._stage
         if nb > chain.nb_max:                                   # a later batch larger than the first: grow, keep the state
             big = _native.BigIPCA(chain.d, chain.c, int(nb), chain.dev)
             big.M[:chain.c].copy_(chain.M[:chain.c])
@@ -77,6 +95,8 @@ class DeviceIncrementalPCA:
         if int(self.n_samples_seen_) == 0 and self.n_components > nb:
             raise ValueError(f"n_components={self.n_components} must be less or equal to the batch number of "
                              f"samples {nb} for the first partial_fit call.")
+        if self._shard is not None:
+            _native.exchange_rows(self._stage, chain.batch_rows(int(nb)), self._shard[1])
         chain.step(int(nb))          # centres the batch rows in place (chain.batch_mean holds the batch mean)
         self.n_samples_seen_ = np.int64(chain.n_seen)
         self._host = None
@@ -117,7 +137,11 @@ class DeviceIncrementalPCA:
 
     def last_batch_mean(self):
         """Large-d engine: fp64 [d] mean of the batch the last partial_fit centred in place."""
-        return self._chain.batch_mean
+        return self._chain.gathered(self._chain.batch_mean.unsqueeze(0)).reshape(-1)
+
+    def last_batch_rows(self, n):
+        """Large-d engine: the first n rows of the last batch as centred by partial_fit, full feature width."""
+        return self._chain.gathered(self._chain.batch_rows(self._chain.last_nb)[:n])
 
     # -- sklearn attribute names (host copies, fetched lazily) ---------------------------------------
     def device_attributes(self):

@@ -212,6 +212,22 @@ size_t gsb_bigd_workspace_bytes(int64_t d, int c, int nb_max);
 int gsb_bigd_reset(void *d_state, float *d_M, int64_t d, int c, int nb_max, gsb_stream_t stream);
 int gsb_bigd_chain_step(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
                         double *d_batch_mean, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
+/* The same step in three phases, for feature-sharded multi-GPU runs: every rank holds a
+ * column block M[:, d_r] (d = its local width) and all NB rows of the batch;
+ *   gsb_bigd_step_gram    centres, merges mean/var, leaves T_r = M_r M_r^T at gsb_bigd_gram_matrix(workspace, ...)
+ *                         ([rows, rows] fp64)  -> the caller all-reduces (sums) T over the ranks
+ *   gsb_bigd_step_solve   eigen-solves T (redundantly on every rank), Dnew_r = U^T M_r, and returns per row
+ *                         (max |.|, its signed value) over the local features in d_rowmax [c,2]
+ *                         -> the caller all-gathers them and picks sklearn's svd_flip sign of the global maximum
+ *   gsb_bigd_step_commit  rows [0,c) <- sign * Dnew_r (d_signs [c]; NULL = local maxima), S, sample count.
+ * gsb_bigd_chain_step == gram; solve; commit(NULL). */
+void *gsb_bigd_gram_matrix(void *d_workspace, int64_t d, int c, int nb_max);
+int gsb_bigd_step_gram(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+                       double *d_batch_mean, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
+int gsb_bigd_step_solve(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+                        float *d_rowmax, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
+int gsb_bigd_step_commit(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+                         const float *d_signs, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
 /* components_ [c,d] as fp32 (any pointer may be NULL); the small vectors and mean_/var_ [d] as fp64 */
 int gsb_bigd_export(const void *d_state, const float *d_M, int64_t d, int c, int64_t n_seen, float *d_components,
                     double *d_singular_values, double *d_mean, double *d_var, double *d_explained_variance,

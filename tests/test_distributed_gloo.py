@@ -78,3 +78,73 @@ def test_sharded_stats_exchange_equals_single_process(tmp_path, oracle):
     for X in _groups(5, pl.K, pl.NB, d):
         oracle.ipca_partial_fit(st2, X)
     assert np.min(np.sum(st2.components * got["comp"], axis=1)) > 1 - 1e-8
+
+
+# ---- feature-sharded large-d chain: row-parallel generation, all-to-all, Gram all-reduce ----------
+def _big_batches(d, nb, k):
+    rng = np.random.RandomState(99)
+    basis = rng.standard_normal((d, 24)).astype(np.float32) * (0.8 ** np.arange(24, dtype=np.float32))[None, :]
+    return [((rng.standard_normal((nb, 24)).astype(np.float32) @ basis.T) + 0.05 * rng.standard_normal((nb, d)).astype(np.float32)
+             + 1.5).astype(np.float32) for _ in range(k)]
+
+
+def _sharded_worker(rank, world, port, out_path):
+    """The protocol of _native.BigIPCA(shard=...).step with numpy standing in for the three device phases."""
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ganspace_b200 import _native
+    d, nb, c, k = 256, 60, 5, 3
+    dl, q = d // world, nb // world
+    D = np.zeros((c, dl), np.float32)
+    mean = np.zeros(dl)
+    n_seen = 0
+    for X in _big_batches(d, nb, k):
+        stage = torch.from_numpy(X[rank * q:(rank + 1) * q].copy())            # this rank's rows, all features
+        rows = torch.empty((nb, dl), dtype=torch.float32)
+        _native.exchange_rows(stage, rows, world)                               # all rows, this rank's feature block
+        assert np.array_equal(rows.numpy(), X[:, rank * dl:(rank + 1) * dl])
+        Xl = rows.numpy().astype(np.float64)
+        mb = Xl.mean(0)
+        corr = np.sqrt(n_seen / (n_seen + nb) * nb) * (mean - mb) if n_seen else np.zeros(dl)
+        M = np.vstack([D, (Xl - mb).astype(np.float32), corr.astype(np.float32)[None]]).astype(np.float64)
+        T = torch.from_numpy(M @ M.T)
+        dist.all_reduce(T)                                                      # phase 1 -> sum over the feature shards
+        lam, U = np.linalg.eigh(T.numpy())
+        lam, U = lam[::-1][:c], U[:, ::-1][:, :c].T
+        Dn = (U @ M).astype(np.float32)                                         # phase 2
+        idx = np.argmax(np.abs(Dn), axis=1)
+        rowmax = torch.from_numpy(np.stack([np.abs(Dn)[np.arange(c), idx], Dn[np.arange(c), idx]], axis=1).astype(np.float32))
+        allmax = torch.empty((world * c, 2))
+        dist.all_gather_into_tensor(allmax, rowmax)
+        signs = _native.pick_global_signs(allmax.view(world, c, 2)).numpy()
+        D = Dn * signs[:, None]                                                 # phase 3
+        S = np.sqrt(lam)
+        mean = (mean * n_seen + mb * nb) / (n_seen + nb)
+        n_seen += nb
+    comp_l = torch.from_numpy((D / S[:, None]).astype(np.float32))
+    full = torch.empty((world * c, dl))
+    dist.all_gather_into_tensor(full, comp_l)
+    if rank == 0:
+        np.savez(out_path, comp=full.view(world, c, dl).permute(1, 0, 2).reshape(c, d).numpy(), sv=S)
+    dist.destroy_process_group()
+
+
+def test_feature_sharded_chain_protocol(tmp_path, oracle):
+    world = 2
+    out_path = str(tmp_path / "fs.npz")
+    mp.spawn(_sharded_worker, args=(world, _free_port(), out_path), nprocs=world, join=True)
+    got = np.load(out_path)
+    st = oracle.IPCAState(5)
+    for X in _big_batches(256, 60, 3):
+        oracle.ipca_partial_fit(st, X)
+    cos = np.sum(got["comp"].astype(np.float64) * st.components, axis=1)
+    assert cos.min() > 1 - 1e-5, cos          # signed: the agreed svd_flip signs match sklearn's
+    assert np.allclose(got["sv"], st.singular_values, rtol=1e-5)
+
+
+def test_pick_global_signs_first_max_rule():
+    from ganspace_b200 import _native
+    allmax = torch.tensor([[[2.0, -2.0], [1.0, 1.0], [3.0, 3.0]],
+                           [[2.0, 2.0], [5.0, -5.0], [3.0, -3.0]]])       # [W=2, c=3, 2]
+    assert _native.pick_global_signs(allmax).tolist() == [-1.0, -1.0, 1.0]   # ties -> lowest shard

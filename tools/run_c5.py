@@ -28,7 +28,14 @@ def main():
     ap.add_argument("--compare")
     ap.add_argument("--sections", action="store_true")
     a = ap.parse_args()
-    dev = torch.device("cuda:0")
+    import os
+    rank, world = 0, 1
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:                     # torchrun: one process per GPU, NCCL
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        dist.init_process_group("nccl")
+        rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
     model = StyleGAN2(dev, "ffhq", random_init=1234)
     inst = get_instrumented_model("StyleGAN2", "ffhq", a.layer, dev, model=model, use_w=False)
     cfg = Config(model="StyleGAN2", layer=a.layer, output_class="ffhq", components=a.c, n=a.n, batch_size=a.b, use_w=False,
@@ -41,9 +48,11 @@ def main():
         path = get_or_compute(cfg, inst, submit_config=SimpleNamespace(run_dir=tmp, run_dir_root=tmp), force_recompute=True)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if rank != 0:
+            return
         with np.load(path) as data:
             out = {k: data[k] for k in data.files}
-    res = {"layer": a.layer, "n": a.n, "b": a.b, "c": a.c, "seconds": dt, "samples_per_s": a.n / dt,
+    res = {"n_gpus": world, "layer": a.layer, "n": a.n, "b": a.b, "c": a.c, "seconds": dt, "samples_per_s": a.n / dt,
            "launches": _native.instrument.launches, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
            "var_ratio_sum": float(out["var_ratio"].sum()), "act_stdev_head": out["act_stdev"][:4].tolist()}
     if a.sections:
