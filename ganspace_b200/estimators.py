@@ -58,9 +58,9 @@ class DeviceIncrementalPCA:
                 self._chain = _native.BigIPCA(d, self.n_components, nb, device, shard=self._shard)
             else:
                 self._chain = _native.IPCAChain(d, self.n_components, device)
-        elif self._chain.d != d:
+        elif getattr(self._chain, "d_full", self._chain.d) != d:     # (a feature-sharded engine's .d is its local width)
             raise ValueError("Number of input features has changed from %i to %i between calls to partial_fit!"
-                             % (self._chain.d, d))
+                             % (getattr(self._chain, "d_full", self._chain.d), d))
         return self._chain
 
     @property
