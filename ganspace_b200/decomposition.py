@@ -172,7 +172,12 @@ def compute(config, dump_name, instrumented_model):
     """decomposition.compute (:150-358): run the pipeline, rank 0 writes the 8-array .npz."""
     timestamp = lambda: datetime.datetime.now().strftime("%d.%m %H:%M")
     print(f"[{timestamp()}] Computing", dump_name.name)
-    arrays = compute_arrays(config, instrumented_model)
+    state = {}
+    arrays = compute_arrays(config, instrumented_model, state)
+    if state.get("canceled_at") is not None:
+        # Ctrl-C during the fitting loop: the reference saves what was fitted so far under n{gi} and exits 1 (:268-274,342-343)
+        dump_name = dump_name.parent / dump_name.name.replace(f"n{state['N']}", f"n{state['canceled_at']}")
+        print(f'Saving current state to "{dump_name.name}" before exiting')
     rank, world, live = _dist()
     if rank == 0:
         os.makedirs(dump_name.parent, exist_ok=True)
@@ -183,6 +188,8 @@ def compute(config, dump_name, instrumented_model):
     if live:
         import torch.distributed as dist
         dist.barrier()
+    if state.get("canceled_at") is not None:
+        sys.exit(1)
 
 
 def _phase_timer():
@@ -200,10 +207,13 @@ def _phase_timer():
     return tick
 
 
-def compute_arrays(config, instrumented_model):
-    """Everything of compute() up to (not including) the file write; returns the 8 float32 arrays."""
+def compute_arrays(config, instrumented_model, state=None):
+    """Everything of compute() up to (not including) the file write; returns the 8 float32 arrays.
+    ``state`` (optional dict) receives N and, after a KeyboardInterrupt in the fitting loop, ``canceled_at`` = the
+    number of samples fitted so far (single-process runs; the result then describes that prefix of the chain)."""
     global B
     tick = _phase_timer()
+    state = {} if state is None else state
 
     torch.manual_seed(0)
     np.random.seed(0)
@@ -284,60 +294,67 @@ def compute_arrays(config, instrumented_model):
     slots = torch.zeros((K, _plan.slot_width(d)), dtype=torch.float64, device=device) if (live and not large_d) else None
     X = None
     tr = transformer.transformer
-    for c0 in range(0, K, groups_per_chunk):
-        if large_d:                              # every rank takes part in every group (its row range)
-            mine = list(range(c0, min(c0 + groups_per_chunk, K)))
-        else:
-            mine = _plan.groups_to_process(pl, rank, world, c0, min(c0 + groups_per_chunk, K))
-        runs = _plan.contiguous_runs(mine)
-        # every sample_latent call this rank needs for the chunk, generated by ONE launch (one CTA per seed)
-        needed, offsets = _plan.batch_slots(pl, runs)
-        lat, ensure_rows = _sample_batches_lazy(model, B, [seeds[b] for b in needed])
-        lat = lat.reshape(lat.shape[0], -1)
-        for run, off in zip(runs, offsets):
-            for k in run:
-                r = off + (k - run[0]) * NB
-                ensure_rows(r + NB)
-                rows = lat[r:r + NB]
-                if samples_are_latents:
-                    X = rows
-                elif affine is not None:
-                    X = affine.coords(rows)
-                elif large_d:
-                    X = tr.batch_buffer(NB, d, device)              # rows of the engine's stacked matrix, in HBM
-                    lo, hi = (rank * (NB // world), (rank + 1) * (NB // world)) if live else (0, NB)   # this rank's rows
-                    for mb in range(0, NB, B):
-                        a, b_ = max(mb, lo), min(mb + min(B, NB - mb), hi)
-                        if a >= b_:
-                            continue
-                        z = rows[a:b_].reshape(-1, *input_shape[1:])
-                        if layout is not None:
-                            model.activations_into(z, layer_key, X[a - lo:b_ - lo])
-                        else:
+    state["N"] = N
+    k = 0
+    try:
+        for c0 in range(0, K, groups_per_chunk):
+            if large_d:                              # every rank takes part in every group (its row range)
+                mine = list(range(c0, min(c0 + groups_per_chunk, K)))
+            else:
+                mine = _plan.groups_to_process(pl, rank, world, c0, min(c0 + groups_per_chunk, K))
+            runs = _plan.contiguous_runs(mine)
+            # every sample_latent call this rank needs for the chunk, generated by ONE launch (one CTA per seed)
+            needed, offsets = _plan.batch_slots(pl, runs)
+            lat, ensure_rows = _sample_batches_lazy(model, B, [seeds[b] for b in needed])
+            lat = lat.reshape(lat.shape[0], -1)
+            for run, off in zip(runs, offsets):
+                for k in run:
+                    r = off + (k - run[0]) * NB
+                    ensure_rows(r + NB)
+                    rows = lat[r:r + NB]
+                    if samples_are_latents:
+                        X = rows
+                    elif affine is not None:
+                        X = affine.coords(rows)
+                    elif large_d:
+                        X = tr.batch_buffer(NB, d, device)              # rows of the engine's stacked matrix, in HBM
+                        lo, hi = (rank * (NB // world), (rank + 1) * (NB // world)) if live else (0, NB)   # this rank's rows
+                        for mb in range(0, NB, B):
+                            a, b_ = max(mb, lo), min(mb + min(B, NB - mb), hi)
+                            if a >= b_:
+                                continue
+                            z = rows[a:b_].reshape(-1, *input_shape[1:])
+                            if layout is not None:
+                                model.activations_into(z, layer_key, X[a - lo:b_ - lo])
+                            else:
+                                with torch.no_grad():
+                                    model.partial_forward(z, layer_key)
+                                X[a - lo:b_ - lo] = inst.retained_features()[layer_key].reshape((z.shape[0], -1))
+                        if not transformer.fit_partial_inplace(NB):
+                            break
+                        continue
+                    else:
+                        X = torch.empty((NB, d), dtype=torch.float32, device=device)
+                        for mb in range(0, NB, B):
+                            z = rows[mb:mb + B].reshape(-1, *input_shape[1:])
                             with torch.no_grad():
                                 model.partial_forward(z, layer_key)
-                            X[a - lo:b_ - lo] = inst.retained_features()[layer_key].reshape((z.shape[0], -1))
-                    if not transformer.fit_partial_inplace(NB):
+                            batch = inst.retained_features()[layer_key].reshape((z.shape[0], -1))
+                            space_left = min(B, NB - mb)
+                            X[mb:mb + space_left] = batch[:space_left]
+                    if live:
+                        if _plan.owner(k, world, K) == rank:
+                            n_b, mean_b, gram_b = tr.batch_stats(X)
+                            slots[k, :d * d] = gram_b.reshape(-1)
+                            slots[k, d * d:] = mean_b
+                    elif not transformer.fit_partial(X):
                         break
-                    continue
-                else:
-                    X = torch.empty((NB, d), dtype=torch.float32, device=device)
-                    for mb in range(0, NB, B):
-                        z = rows[mb:mb + B].reshape(-1, *input_shape[1:])
-                        with torch.no_grad():
-                            model.partial_forward(z, layer_key)
-                        batch = inst.retained_features()[layer_key].reshape((z.shape[0], -1))
-                        space_left = min(B, NB - mb)
-                        X[mb:mb + space_left] = batch[:space_left]
-                if live:
-                    if _plan.owner(k, world, K) == rank:
-                        n_b, mean_b, gram_b = tr.batch_stats(X)
-                        slots[k, :d * d] = gram_b.reshape(-1)
-                        slots[k, d * d:] = mean_b
-                elif not transformer.fit_partial(X):
-                    break
-        ensure_rows(lat.shape[0])
-        del lat    # X (a view of the last group when samples_are_latents) keeps its storage alive
+            ensure_rows(lat.shape[0])
+            del lat    # X (a view of the last group when samples_are_latents) keeps its storage alive
+    except KeyboardInterrupt:
+        if live:
+            raise
+        state["canceled_at"] = int(k) * NB              # the reference's `gi` of the interrupted group (:268-272)
     if live and not large_d:
         import torch.distributed as dist
         dist.all_reduce(slots)                         # the run's single exchange of PCA statistics

@@ -85,3 +85,41 @@ def test_cache_hit_and_validation_errors():
         get_or_compute(Config(model="StyleGAN2", output_class="ffhq", layer="style", n=100), model=object())
     with pytest.raises(RuntimeError, match="Cannot change latent space"):
         get_or_compute(Config(model="BigGAN-512", output_class="husky", layer="generator.gen_z", n=100, use_w=True))
+
+
+def test_keyboard_interrupt_saves_partial_state(oracle, mapping_weights, monkeypatch):
+    """Ctrl-C in the fitting loop: the reference writes the state fitted so far under n{gi} and exits 1
+    (decomposition.py:268-274, 342-343)."""
+    from ganspace_b200 import estimators
+    from ganspace_b200.config import Config
+    from ganspace_b200.decomposition import get_or_compute
+    from ganspace_b200.models import get_instrumented_model, StyleGAN2
+    calls = {"n": 0}
+    orig = estimators.IPCAEstimator.fit_partial
+
+    def interrupting(self, X):
+        calls["n"] += 1
+        if calls["n"] == 3:
+            raise KeyboardInterrupt
+        return orig(self, X)
+
+    monkeypatch.setattr(estimators.IPCAEstimator, "fit_partial", interrupting)
+    dev = torch.device("cuda:0")
+    model = StyleGAN2(dev, "ffhq", random_init=1234)
+    inst = get_instrumented_model("StyleGAN2", "ffhq", "style", dev, model=model, use_w=True)
+    cfg = Config(model="StyleGAN2", layer="style", output_class="ffhq", components=32, n=10_000, batch_size=1_000,
+                 use_w=True, estimator="ipca")
+    with tempfile.TemporaryDirectory() as tmp:
+        with pytest.raises(SystemExit) as ex:
+            get_or_compute(cfg, inst, submit_config=SimpleNamespace(run_dir=tmp, run_dir_root=tmp), force_recompute=True)
+        assert ex.value.code == 1
+        files = sorted(p.name for p in (pytest.importorskip("pathlib").Path(tmp) / "cache" / "components").glob("*.npz"))
+        assert files == ["stylegan2-ffhq_style_ipca_c32_n4000_w.npz"], files
+        with np.load(pytest.importorskip("pathlib").Path(tmp) / "cache" / "components" / files[0]) as data:
+            out = {k: data[k] for k in data.files}
+    inst.close()
+    ref = oracle.compute_stylegan2_style(*mapping_weights, 4_000, 1_000, 32, True)     # the same two groups
+    a = out["act_comp"].reshape(32, -1).astype(np.float64)
+    b = ref["act_comp"].reshape(32, -1).astype(np.float64)
+    assert np.sum(a * b, axis=1).min() >= COS_TOL
+    assert np.abs(out["var_ratio"] - ref["var_ratio"]).max() <= RATIO_TOL
