@@ -51,14 +51,14 @@ SIGNATURES = {
     "gsb_synthesis_status": (_I, [_P, _P, _I, _I, _P]),
     "gsb_bigd_rows": (_I, [_I, _I]),
     "gsb_bigd_state_bytes": (_Z, [_L, _I]),
-    "gsb_bigd_workspace_bytes": (_Z, [_L, _I, _I]),
+    "gsb_bigd_workspace_bytes": (_Z, [_L, _I, _I, _I]),
     "gsb_bigd_reset": (_I, [_P, _P, _L, _I, _I, _P]),
-    "gsb_bigd_chain_step": (_I, [_P, _P, _L, _I, _I, _L, _I, _P, _P, _Z, _P]),
+    "gsb_bigd_chain_step": (_I, [_P, _P, _L, _I, _I, _L, _I, _I, _P, _P, _Z, _P]),
     "gsb_bigd_export": (_I, [_P, _P, _L, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
     "gsb_bigd_gram_matrix": (_P, [_P, _L, _I, _I]),
-    "gsb_bigd_step_gram": (_I, [_P, _P, _L, _I, _I, _L, _I, _P, _P, _Z, _P]),
-    "gsb_bigd_step_solve": (_I, [_P, _P, _L, _I, _I, _L, _I, _P, _P, _Z, _P]),
-    "gsb_bigd_step_commit": (_I, [_P, _P, _L, _I, _I, _L, _I, _P, _P, _Z, _P]),
+    "gsb_bigd_step_gram": (_I, [_P, _P, _L, _I, _I, _L, _I, _I, _P, _P, _Z, _P]),
+    "gsb_bigd_step_solve": (_I, [_P, _P, _L, _I, _I, _L, _I, _I, _P, _P, _Z, _P]),
+    "gsb_bigd_step_commit": (_I, [_P, _P, _L, _I, _I, _L, _I, _I, _P, _P, _Z, _P]),
 }
 
 
@@ -576,9 +576,14 @@ class BigIPCA:
     ``shard=(rank, world)``: feature-sharded over a torch.distributed job -- this object holds the column block
     d/world of M; ``step`` all-reduces the small-side Gram (fp64, (c+nb+1)^2) and agrees on the svd_flip signs."""
 
-    def __init__(self, d: int, c: int, nb_max: int, device, shard=None):
+    def __init__(self, d: int, c: int, nb_max: int, device, shard=None, gram: str = None):
         lib = load()
         self.dev = require_cuda(device)
+        # small-side Gram kernel: "simt" = fp32 FMA (default), "tc" = tcgen05 with a promoted accumulator (gram_tc.cu)
+        gram = gram or os.environ.get("GANSPACE_B200_BIGD_GRAM", "simt")
+        if gram not in ("simt", "tc"):
+            raise NativeError(f"unknown Gram kernel '{gram}' (simt | tc)")
+        self.flags = 1 if gram == "tc" else 0
         self.shard = shard if (shard is not None and shard[1] > 1) else None
         self.d_full = int(d)
         if self.shard is not None:
@@ -586,7 +591,7 @@ class BigIPCA:
                 raise NativeError(f"feature sharding needs d % (16*world) == 0 (d={d}, world={self.shard[1]})")
             d = d // self.shard[1]
         self.d, self.c, self.nb_max = int(d), int(c), int(nb_max)
-        ws_bytes = lib.gsb_bigd_workspace_bytes(self.d, self.c, self.nb_max)
+        ws_bytes = lib.gsb_bigd_workspace_bytes(self.d, self.c, self.nb_max, self.flags)
         if ws_bytes == 0:
             raise NativeError(f"gsb_bigd_workspace_bytes: {lib.gsb_last_error().decode()}")
         self.rows = lib.gsb_bigd_rows(self.c, self.nb_max)
@@ -598,18 +603,24 @@ class BigIPCA:
         self.last_nb = 0
         with torch.cuda.device(self.dev):
             _check(lib.gsb_bigd_reset(_ptr(self.state), _ptr(self.M), self.d, self.c, self.nb_max, _stream()), "gsb_bigd_reset")
-        if self.shard is not None:
-            t_ptr = lib.gsb_bigd_gram_matrix(_ptr(self.ws), self.d, self.c, self.nb_max)
-            off = int(t_ptr) - self.ws.data_ptr()
-            self._T = self.ws[off:off + self.rows * self.rows * 8].view(torch.float64)
-            self._rowmax = torch.empty((self.c, 2), dtype=torch.float32, device=self.dev)
+        t_ptr = lib.gsb_bigd_gram_matrix(_ptr(self.ws), self.d, self.c, self.nb_max)
+        off = int(t_ptr) - self.ws.data_ptr()
+        self._T = self.ws[off:off + self.rows * self.rows * 8].view(torch.float64)      # small-side Gram [rows, rows]
+        self._rowmax = torch.empty((self.c, 2), dtype=torch.float32, device=self.dev)
 
     def batch_rows(self, nb: int) -> torch.Tensor:
         assert 1 <= nb <= self.nb_max
         return self.M[self.c:self.c + nb]
 
     def _args(self, nb):
-        return (_ptr(self.state), _ptr(self.M), self.d, self.c, self.nb_max, self.n_seen, int(nb))
+        return (_ptr(self.state), _ptr(self.M), self.d, self.c, self.nb_max, self.n_seen, int(nb), self.flags)
+
+    def gram_only(self, nb: int) -> torch.Tensor:
+        """Test hook: phase 1 alone (centres the batch rows!); returns the small-side Gram [rows, rows] fp64."""
+        with torch.cuda.device(self.dev):
+            _check(load().gsb_bigd_step_gram(*self._args(nb), _ptr(self.batch_mean), _ptr(self.ws), self.ws.numel(), _stream()),
+                   "gsb_bigd_step_gram")
+        return self._T.view(self.rows, self.rows)
 
     def step(self, nb: int):
         lib = load()
@@ -628,7 +639,7 @@ class BigIPCA:
                 _check(lib.gsb_bigd_step_commit(*self._args(nb), _ptr(signs), *tail), "gsb_bigd_step_commit")
         lanczos = (os.environ.get("GANSPACE_B200_BIGD_CHAIN") == "lanczos" and self.n_seen > 0 and self.c % 16 == 0
                    and self.c <= 128 and 3 * self.c <= self.rows // 2 + self.rows // 8)
-        instrument.count(7 + (37 if lanczos else 5))
+        instrument.count(7 + (37 if lanczos else 5) + (2 if self.flags & 1 else 0))
         self.n_seen += int(nb)
         self.last_nb = int(nb)
 

@@ -24,6 +24,11 @@
 
 namespace gsb {
 
+// tensor-core small-side Gram (gram_tc.cu)
+size_t gram_tc_workspace_bytes(int n_pad, int64_t d);
+bool gram_tc_supported(int64_t d);
+int gram_tc(const float *M, int n_rows, int n_pad, int64_t d, void *ws, double *T, cudaStream_t st);
+
 constexpr int BD_HDR = 4;
 constexpr int BD_KCHUNK = 8192;
 
@@ -57,10 +62,11 @@ struct BigWs {
     void *lan;
     double *mean_b, *E, *U, *lam;
     float *Dnew, *rowmax;
+    void *tc;              // operands of the tensor-core Gram (flags & GSB_BIGD_GRAM_TC)
     size_t bytes;
     bool lanczos;
 };
-static BigWs big_ws(void *base, int64_t d, int c, int nb_max) {
+static BigWs big_ws(void *base, int64_t d, int c, int nb_max, int flags) {
     BigWs w;
     const int np = bigd_rows(c, nb_max);
     char *p = reinterpret_cast<char *>(base);
@@ -76,6 +82,7 @@ static BigWs big_ws(void *base, int64_t d, int c, int nb_max) {
     w.lam = (double *)take((size_t)c * 8);
     w.Dnew = (float *)take((size_t)c * d * 4);
     w.rowmax = (float *)take((size_t)2 * c * 4);
+    w.tc = ((flags & GSB_BIGD_GRAM_TC) && gram_tc_supported(d)) ? take(gram_tc_workspace_bytes(np, d)) : nullptr;
     w.bytes = off;
     return w;
 }
@@ -360,9 +367,9 @@ extern "C" int gsb_bigd_rows(int c, int nb_max) { return gsb::bigd_rows(c, nb_ma
 
 extern "C" size_t gsb_bigd_state_bytes(int64_t d, int c) { return (size_t)(gsb::BD_HDR + 2 * (size_t)d + c) * sizeof(double); }
 
-extern "C" size_t gsb_bigd_workspace_bytes(int64_t d, int c, int nb_max) {
+extern "C" size_t gsb_bigd_workspace_bytes(int64_t d, int c, int nb_max, int flags) {
     if (gsb::bigd_check(d, c, nb_max)) return 0;
-    return gsb::big_ws(nullptr, d, c, nb_max).bytes;
+    return gsb::big_ws(nullptr, d, c, nb_max, flags).bytes;
 }
 
 extern "C" int gsb_bigd_reset(void *d_state, float *d_M, int64_t d, int c, int nb_max, gsb_stream_t stream) {
@@ -376,13 +383,13 @@ extern "C" int gsb_bigd_reset(void *d_state, float *d_M, int64_t d, int c, int n
 
 namespace gsb {
 struct StepCtx { BigWs w; BigState s; int np, n_rows; cudaStream_t st; };
-static int step_ctx(StepCtx &x, void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb, void *d_workspace,
-                    size_t workspace_bytes, gsb_stream_t stream) {
+static int step_ctx(StepCtx &x, void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb, int flags,
+                    void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
     GSB_CHECK_ARG(d_state && d_M && d_workspace, "bigd step: null pointer");
     if (int r = bigd_check(d, c, nb_max)) return r;
     GSB_CHECK_ARG(nb >= 1 && nb <= nb_max && n_seen >= 0, "bigd step: bad batch size %d (nb_max=%d)", nb, nb_max);
     GSB_CHECK_ARG(n_seen > 0 || c <= nb, "bigd step: n_components=%d > first batch size %d", c, nb);
-    x.w = big_ws(d_workspace, d, c, nb_max);
+    x.w = big_ws(d_workspace, d, c, nb_max, flags);
     if (workspace_bytes < x.w.bytes) { set_error("bigd step: workspace too small (%zu < %zu)", workspace_bytes, x.w.bytes); return GSB_ERR_WORKSPACE; }
     x.s = big_state(d_state, d, c);
     x.np = bigd_rows(c, nb_max);
@@ -394,20 +401,21 @@ static int step_ctx(StepCtx &x, void *d_state, float *d_M, int64_t d, int c, int
 
 extern "C" void *gsb_bigd_gram_matrix(void *d_workspace, int64_t d, int c, int nb_max) {
     if (!d_workspace || gsb::bigd_check(d, c, nb_max)) return nullptr;
-    return gsb::big_ws(d_workspace, d, c, nb_max).ew.A;
+    return gsb::big_ws(d_workspace, d, c, nb_max, 0).ew.A;         // T is the first block of the workspace for any flags
 }
 
 // phase 1: centre the batch rows, update mean / variance, T = M M^T over THIS device's features
-extern "C" int gsb_bigd_step_gram(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+extern "C" int gsb_bigd_step_gram(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb, int flags,
                                   double *d_batch_mean, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
     using namespace gsb;
     StepCtx x;
-    if (int r = step_ctx(x, d_state, d_M, d, c, nb_max, n_seen, nb, d_workspace, workspace_bytes, stream)) return r;
+    if (int r = step_ctx(x, d_state, d_M, d, c, nb_max, n_seen, nb, flags, d_workspace, workspace_bytes, stream)) return r;
     bigd_center_kernel<<<(unsigned)((d + 255) / 256), 256, 0, x.st>>>(d_M, d, c, nb, x.np, (double)n_seen, x.s.mean, x.s.unnorm, x.w.mean_b);
     GSB_CHECK_LAUNCH();
     if (d_batch_mean) GSB_CHECK_CUDA(cudaMemcpyAsync(d_batch_mean, x.w.mean_b, (size_t)d * sizeof(double), cudaMemcpyDeviceToDevice, x.st));
     double *T = x.w.ew.A;
     GSB_CHECK_CUDA(cudaMemsetAsync(T, 0, (size_t)x.np * x.np * sizeof(double), x.st));
+    if (x.w.tc) return gram_tc(d_M, x.n_rows, x.np, d, x.w.tc, T, x.st);      // tcgen05, promoted accumulator (gram_tc.cu)
     const int nt = (x.n_rows + GB - 1) / GB;
     dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)((d + BD_KCHUNK - 1) / BD_KCHUNK));
     bigd_gram_kernel<<<grid, 256, 0, x.st>>>(d_M, x.n_rows, d, BD_KCHUNK, T, x.np);
@@ -416,11 +424,11 @@ extern "C" int gsb_bigd_step_gram(void *d_state, float *d_M, int64_t d, int c, i
 }
 
 // phase 2: top-c eigenpairs of T (summed over the feature shards by the caller), Dnew = U^T M, per-row maxima
-extern "C" int gsb_bigd_step_solve(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+extern "C" int gsb_bigd_step_solve(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb, int flags,
                                    float *d_rowmax, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
     using namespace gsb;
     StepCtx x;
-    if (int r = step_ctx(x, d_state, d_M, d, c, nb_max, n_seen, nb, d_workspace, workspace_bytes, stream)) return r;
+    if (int r = step_ctx(x, d_state, d_M, d, c, nb_max, n_seen, nb, flags, d_workspace, workspace_bytes, stream)) return r;
     double *T = x.w.ew.A;
     if (n_seen > 0 && x.w.lanczos) {
         bigd_unit_rows_kernel<<<(c * x.np + 255) / 256, 256, 0, x.st>>>(x.w.E, c, x.np);
@@ -439,21 +447,21 @@ extern "C" int gsb_bigd_step_solve(void *d_state, float *d_M, int64_t d, int c, 
 }
 
 // phase 3: commit  S*Vt <- sign * Dnew  (d_signs [c], or NULL = this device's own row maxima), S, sample count
-extern "C" int gsb_bigd_step_commit(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+extern "C" int gsb_bigd_step_commit(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb, int flags,
                                     const float *d_signs, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
     using namespace gsb;
     StepCtx x;
-    if (int r = step_ctx(x, d_state, d_M, d, c, nb_max, n_seen, nb, d_workspace, workspace_bytes, stream)) return r;
+    if (int r = step_ctx(x, d_state, d_M, d, c, nb_max, n_seen, nb, flags, d_workspace, workspace_bytes, stream)) return r;
     bigd_commit_kernel<<<c, 1024, 0, x.st>>>(x.w.Dnew, d, x.w.lam, x.w.rowmax, d_signs, d_M, x.s.S, x.s.hdr, (double)(n_seen + nb));
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }
 
-extern "C" int gsb_bigd_chain_step(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+extern "C" int gsb_bigd_chain_step(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb, int flags,
                                    double *d_batch_mean, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
-    if (int r = gsb_bigd_step_gram(d_state, d_M, d, c, nb_max, n_seen, nb, d_batch_mean, d_workspace, workspace_bytes, stream)) return r;
-    if (int r = gsb_bigd_step_solve(d_state, d_M, d, c, nb_max, n_seen, nb, nullptr, d_workspace, workspace_bytes, stream)) return r;
-    return gsb_bigd_step_commit(d_state, d_M, d, c, nb_max, n_seen, nb, nullptr, d_workspace, workspace_bytes, stream);
+    if (int r = gsb_bigd_step_gram(d_state, d_M, d, c, nb_max, n_seen, nb, flags, d_batch_mean, d_workspace, workspace_bytes, stream)) return r;
+    if (int r = gsb_bigd_step_solve(d_state, d_M, d, c, nb_max, n_seen, nb, flags, nullptr, d_workspace, workspace_bytes, stream)) return r;
+    return gsb_bigd_step_commit(d_state, d_M, d, c, nb_max, n_seen, nb, flags, nullptr, d_workspace, workspace_bytes, stream);
 }
 
 extern "C" int gsb_bigd_export(const void *d_state, const float *d_M, int64_t d, int c, int64_t n_seen, float *d_components,

@@ -83,7 +83,7 @@ class DeviceIncrementalPCA:
                 self._stage = torch.empty((q, int(d)), dtype=torch.float32, device=chain.dev)
             return self._stage
         if nb > chain.nb_max:                                   # a later batch larger than the first: grow, keep the state
-            big = _native.BigIPCA(chain.d, chain.c, int(nb), chain.dev)
+            big = _native.BigIPCA(chain.d, chain.c, int(nb), chain.dev, gram="tc" if chain.flags & 1 else "simt")
             big.M[:chain.c].copy_(chain.M[:chain.c])
             big.state.copy_(chain.state)
             big.n_seen = chain.n_seen

@@ -208,9 +208,11 @@ int gsb_synthesis_status(const void *d_packed, const gsb_styled_conv *layers, in
  * ---------------------------------------------------------------------------------------------- */
 int gsb_bigd_rows(int c, int nb_max);
 size_t gsb_bigd_state_bytes(int64_t d, int c);
-size_t gsb_bigd_workspace_bytes(int64_t d, int c, int nb_max);
+#define GSB_BIGD_GRAM_TC 1   /* flags: small-side Gram on tcgen05 (fp16 hi/lo split, accumulator promoted every K = 256);
+                                default 0 = fp32 FMA kernel.  The same flags go to the workspace query and every phase. */
+size_t gsb_bigd_workspace_bytes(int64_t d, int c, int nb_max, int flags);
 int gsb_bigd_reset(void *d_state, float *d_M, int64_t d, int c, int nb_max, gsb_stream_t stream);
-int gsb_bigd_chain_step(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+int gsb_bigd_chain_step(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb, int flags,
                         double *d_batch_mean, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
 /* The same step in three phases, for feature-sharded multi-GPU runs: every rank holds a
  * column block M[:, d_r] (d = its local width) and all NB rows of the batch;
@@ -222,11 +224,11 @@ int gsb_bigd_chain_step(void *d_state, float *d_M, int64_t d, int c, int nb_max,
  *   gsb_bigd_step_commit  rows [0,c) <- sign * Dnew_r (d_signs [c]; NULL = local maxima), S, sample count.
  * gsb_bigd_chain_step == gram; solve; commit(NULL). */
 void *gsb_bigd_gram_matrix(void *d_workspace, int64_t d, int c, int nb_max);
-int gsb_bigd_step_gram(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+int gsb_bigd_step_gram(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb, int flags,
                        double *d_batch_mean, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
-int gsb_bigd_step_solve(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+int gsb_bigd_step_solve(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb, int flags,
                         float *d_rowmax, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
-int gsb_bigd_step_commit(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb,
+int gsb_bigd_step_commit(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb, int flags,
                          const float *d_signs, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
 /* components_ [c,d] as fp32 (any pointer may be NULL); the small vectors and mean_/var_ [d] as fp64 */
 int gsb_bigd_export(const void *d_state, const float *d_M, int64_t d, int c, int64_t n_seen, float *d_components,

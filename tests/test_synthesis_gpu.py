@@ -115,11 +115,44 @@ def _synthetic_batches(d, nb, k, seed):
              + shift).astype(np.float32) for _ in range(k)]
 
 
+def test_gram_tc_matches_fp64(monkeypatch):
+    """Small-side Gram on tcgen05 with the promoted accumulator vs the fp32-FMA kernel vs fp64, three chunks of d with a
+    ragged tail, rows of very different magnitude (per-row power-of-two scaling)."""
+    from ganspace_b200 import _native
+    dev = torch.device("cuda:0")
+    d, nb, c = 20480, 300, 12
+    g = torch.Generator(device="cpu").manual_seed(3)
+    base = torch.randn(nb + c, d, generator=g)
+    base[:c] *= 1000.0                       # "S * Vt" rows
+    base[c + 5] *= 1e-3
+    base[c + 6] *= 50.0
+    base[c:] += 0.7                          # non-zero batch mean
+    res = {}
+    for gram in ("simt", "tc"):
+        eng = _native.BigIPCA(d, c, nb, dev, gram=gram)
+        eng.M[:c].copy_(base[:c])
+        eng.batch_rows(nb).copy_(base[c:])
+        eng.n_seen = 900                      # a previous state: the correction row is live
+        T = eng.gram_only(nb).clone()
+        M64 = eng.M[:c + nb + 1].double()     # centred in place by phase 1
+        ref = M64 @ M64.T
+        n = c + nb + 1
+        scale = torch.sqrt(torch.outer(torch.diag(ref), torch.diag(ref)))
+        res[gram] = float(((T[:n, :n] - ref).abs() / scale).max())
+        assert float(((T[:n, :n] - T[:n, :n].T).abs() / scale).max()) < 1e-12
+        assert float(T[n:].abs().max()) == 0.0 and float(T[:, n:].abs().max()) == 0.0
+    print("gram error vs fp64 (relative to sqrt(T_ii T_jj)):", res)
+    assert res["simt"] < 2e-6, res
+    assert res["tc"] < 6e-6, res
+
+
+@pytest.mark.parametrize("gram", ["simt", "tc"])
 @pytest.mark.parametrize("d,nb,c,k", [(4096, 300, 12, 4), (2048, 1100, 16, 3)])
-def test_large_d_chain_vs_sklearn_form(oracle, d, nb, c, k):
+def test_large_d_chain_vs_sklearn_form(oracle, monkeypatch, d, nb, c, k, gram):
     """IPCAEstimator with d > 1024 (small-side engine) against the oracle's restatement of IncrementalPCA.partial_fit.
     (2048, 1100, 16): small side 1117 -> 1120 > 1024 exercises the L2 eigensolver on step 0 and the Lanczos steps after."""
     from ganspace_b200.estimators import get_estimator
+    monkeypatch.setenv("GANSPACE_B200_BIGD_GRAM", gram)
     Xs = _synthetic_batches(d, nb, k, seed=d + nb)
     est = get_estimator("ipca", c, 1.0)
     st = oracle.IPCAState(c)
