@@ -208,8 +208,9 @@ int gsb_synthesis_status(const void *d_packed, const gsb_styled_conv *layers, in
  * ---------------------------------------------------------------------------------------------- */
 int gsb_bigd_rows(int c, int nb_max);
 size_t gsb_bigd_state_bytes(int64_t d, int c);
-#define GSB_BIGD_GRAM_TC 1   /* flags: small-side Gram on tcgen05 (fp16 hi/lo split, accumulator promoted every K = 256);
-                                default 0 = fp32 FMA kernel.  The same flags go to the workspace query and every phase. */
+#define GSB_BIGD_GRAM_TC 1   /* flags: small-side Gram on tcgen05 (fp16 hi/lo split, accumulator promoted every K = 256; needs
+                                d % 64 == 0, else the fp32 FMA kernel runs); 0 = fp32 FMA kernel.  The host mirror passes
+                                GSB_BIGD_GRAM_TC by default.  The same flags go to the workspace query and every phase. */
 size_t gsb_bigd_workspace_bytes(int64_t d, int c, int nb_max, int flags);
 int gsb_bigd_reset(void *d_state, float *d_M, int64_t d, int c, int nb_max, gsb_stream_t stream);
 int gsb_bigd_chain_step(void *d_state, float *d_M, int64_t d, int c, int nb_max, int64_t n_seen, int nb, int flags,
