@@ -585,6 +585,35 @@ def styled_conv_forward(x, w, L, noise):
     return out.numpy()
 
 
+def styled_conv_shared(x, w, L, noise):
+    """styled_conv_forward with the per-sample weights factored out (identical algebra, used for bulk oracle runs: the
+    reference form builds a [B,co,ci,3,3] weight tensor per call): scale the input channels by the style, convolve with
+    the SHARED scale*W through the same torch CPU conv kernels, multiply by demod afterwards (the blur is linear and
+    per-channel, so the demodulation commutes with it)."""
+    import math
+    import torch
+    import torch.nn.functional as F
+    x = torch.from_numpy(np.ascontiguousarray(x, np.float32))
+    w = torch.from_numpy(np.ascontiguousarray(w, np.float32))
+    W = torch.from_numpy(L["weight"]) * (1 / math.sqrt(L["weight"].shape[1] * 9))            # [co,ci,3,3]
+    B, ci, H, _ = x.shape
+    style = F.linear(w, torch.from_numpy(L["mod_weight"]) * (1 / math.sqrt(512)), bias=torch.from_numpy(L["mod_bias"]))
+    demod = torch.rsqrt((style * style) @ (W * W).sum([2, 3]).T + 1e-8)                       # [B,co]
+    xs = x * style.view(B, ci, 1, 1)
+    if L["upsample"]:
+        out = F.conv_transpose2d(xs, W.transpose(0, 1), padding=0, stride=2)                   # [B,co,2H+1,2H+1]
+        co = out.shape[1]
+        out = F.pad(out, [1, 1, 1, 1]).reshape(B * co, 1, 2 * H + 3, 2 * H + 3)
+        kflip = torch.flip(torch.from_numpy(BLUR_K2D), [0, 1]).view(1, 1, 4, 4)
+        out = F.conv2d(out, kflip).view(B, co, 2 * H, 2 * H)
+    else:
+        out = F.conv2d(xs, W, padding=1)
+    out = out * demod.view(B, -1, 1, 1)
+    out = out + torch.tensor(float(L["noise_weight"])) * torch.from_numpy(np.asarray(noise, np.float32))[None, None]
+    out = (2 ** 0.5) * F.leaky_relu(out + torch.from_numpy(L["act_bias"]).view(1, -1, 1, 1), negative_slope=0.2)
+    return out.numpy()
+
+
 def styled_conv_taps(x_nhwc, w, L, noise):
     """The same StyledConv in the form the CUDA path uses (numpy, float64 accumulation): scale the INPUT channels by
     the style, one dense contraction per 3x3 tap with the shared weights (Y[b,p,tap,co] = sum_ci W[co,ci,tap] xs[b,p,ci]),
@@ -632,12 +661,13 @@ def synthesis_forward(w, params, noises, upto: str, form: str = "reference"):
         x = x.transpose(0, 2, 3, 1)
     for idx, name in enumerate(synthesis_layer_names(upto)):
         L = params["layers"][name]
-        x = styled_conv_forward(x, w, L, noises[idx]) if form == "reference" else styled_conv_taps(x, w, L, noises[idx])
-    return x if form == "reference" else x.transpose(0, 3, 1, 2)
+        fn = {"reference": styled_conv_forward, "shared": styled_conv_shared, "taps": styled_conv_taps}[form]
+        x = fn(x, w, L, noises[idx])
+    return x.transpose(0, 3, 1, 2) if form == "taps" else x
 
 
 def compute_stylegan2_layer(weights, biases, params, layer: str, n: int, B: int, c: int, size: int = 1024, seed=None,
-                            return_aux: bool = False, regress: bool = True):
+                            return_aux: bool = False, regress: bool = True, form: str = "shared"):
     """model=StyleGAN2, layer=conv1|convs.k, Z space (decomposition.py:150-341): activations = synthesis(mapping(z))
     flattened NCHW; IncrementalPCA in its sklearn (stacked-SVD) form; regression back to z."""
     noises = fixed_noise(0, size)
@@ -645,8 +675,8 @@ def compute_stylegan2_layer(weights, biases, params, layer: str, n: int, B: int,
 
     def activate(z):
         out = []
-        for i in range(0, z.shape[0], 64):
-            out.append(synthesis_forward(mapping_forward(z[i:i + 64], weights, biases), params, noises, layer))
+        for i in range(0, z.shape[0], 256):
+            out.append(synthesis_forward(mapping_forward(z[i:i + 256], weights, biases), params, noises, layer, form=form))
         a = np.concatenate(out, axis=0)
         return a.reshape(a.shape[0], -1)
 

@@ -120,6 +120,9 @@ def test_synthesis_tap_form_equals_reference_form(oracle):
     a = oracle.synthesis_forward(w, p, noises, "convs.2")
     b = oracle.synthesis_forward(w, p, noises, "convs.2", form="taps")
     assert np.abs(a - b).max() < 5e-5 * np.abs(a).max()
+    # and the shared-weight torch form used for bulk oracle runs (compute_stylegan2_layer)
+    c = oracle.synthesis_forward(w, p, noises, "convs.2", form="shared")
+    assert np.abs(a - c).max() < 5e-5 * np.abs(a).max()
 
 
 def test_conv_layer_pca_restatement_vs_reference(oracle, golden, mapping_weights):
