@@ -23,6 +23,42 @@ def test_library_exports_every_declared_symbol():
     assert _native.load().gsb_abi_version() == 1
 
 
+def test_ctypes_signatures_match_header_prototypes():
+    """Every prototype of include/ganspace_b200.h against the ctypes signature the host mirror binds: same arity and
+    the same C scalar class per argument (pointer / int / int64 / size_t / double / float) and return type."""
+    import ctypes as C
+    from ganspace_b200 import _native
+    header = (ROOT / "include" / "ganspace_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)                     # strip comments
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(gsb_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) == len(_native.SIGNATURES)
+
+    def classify(decl):
+        decl = decl.strip()
+        if decl in ("void", ""):
+            return None
+        if "*" in decl or "gsb_stream_t" in decl:
+            return C.c_void_p
+        for key, ct in (("int64_t", C.c_int64), ("size_t", C.c_size_t), ("double", C.c_double), ("float", C.c_float),
+                        ("unsigned", C.c_uint), ("int", C.c_int)):
+            if re.search(rf"\b{key}\b", decl):
+                return ct
+        raise AssertionError(f"unclassified C type: {decl!r}")
+
+    for ret, name, args in protos:
+        res, argtypes = _native.SIGNATURES[name]
+        want = [classify(a) for a in args.split(",")]
+        want = [w for w in want if w is not None]
+        assert len(want) == len(argtypes), (name, len(want), len(argtypes))
+        for i, (w, a) in enumerate(zip(want, argtypes)):
+            assert w is a, (name, i, w, a)
+        rw = classify(ret)
+        if name == "gsb_last_error":
+            assert res is C.c_char_p
+        else:
+            assert rw is res, (name, rw, res)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback():
     from ganspace_b200 import _native
