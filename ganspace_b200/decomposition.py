@@ -296,8 +296,11 @@ def compute_arrays(config, instrumented_model, state=None):
     tr = transformer.transformer
     state["N"] = N
     k = 0
+    stop = False                 # fit_partial returned False (e.g. n_components > first batch): the reference leaves the loop (:262-263)
     try:
         for c0 in range(0, K, groups_per_chunk):
+            if stop:
+                break
             if large_d:                              # every rank takes part in every group (its row range)
                 mine = list(range(c0, min(c0 + groups_per_chunk, K)))
             else:
@@ -308,6 +311,8 @@ def compute_arrays(config, instrumented_model, state=None):
             lat, ensure_rows = _sample_batches_lazy(model, B, [seeds[b] for b in needed])
             lat = lat.reshape(lat.shape[0], -1)
             for run, off in zip(runs, offsets):
+                if stop:
+                    break
                 for k in run:
                     r = off + (k - run[0]) * NB
                     ensure_rows(r + NB)
@@ -331,6 +336,7 @@ def compute_arrays(config, instrumented_model, state=None):
                                     model.partial_forward(z, layer_key)
                                 X[a - lo:b_ - lo] = inst.retained_features()[layer_key].reshape((z.shape[0], -1))
                         if not transformer.fit_partial_inplace(NB):
+                            stop = True
                             break
                         continue
                     else:
@@ -348,6 +354,7 @@ def compute_arrays(config, instrumented_model, state=None):
                             slots[k, :d * d] = gram_b.reshape(-1)
                             slots[k, d * d:] = mean_b
                     elif not transformer.fit_partial(X):
+                        stop = True
                         break
             ensure_rows(lat.shape[0])
             del lat    # X (a view of the last group when samples_are_latents) keeps its storage alive
