@@ -461,7 +461,7 @@ def compare_npz(ours: dict, ref: dict) -> dict:
     lcos = np.sum(la * lb, axis=1) / (np.linalg.norm(la, axis=1) * np.linalg.norm(lb, axis=1))
 
     def rel(k):
-        x, y = np.asarray(ours[k], np.float64), np.asarray(ref[k], np.float64)
+        x, y = np.asarray(ours[k], np.float64).ravel(), np.asarray(ref[k], np.float64).ravel()   # [1,C,H,W] vs [1,d] layouts
         return float(np.max(np.abs(x - y)) / max(np.max(np.abs(y)), 1e-30))
 
     return {

@@ -151,85 +151,14 @@ def test_pick_global_signs_first_max_rule():
 
 
 # ---- the estimator's sharded host logic (batch_buffer / partial_fit_inplace / gathers) with a CPU stand-in engine ---------
-class _FakeBig:
-    """CPU stand-in for _native.BigIPCA with the same interface (numpy phases, gloo collectives)."""
-
-    def __init__(self, d, c, nb_max, device, shard=None):
-        self.shard = shard if (shard is not None and shard[1] > 1) else None
-        self.d_full = int(d)
-        W = self.shard[1] if self.shard else 1
-        self.d, self.c, self.nb_max, self.dev = int(d) // W, int(c), int(nb_max), torch.device("cpu")
-        self.rows = c + nb_max + 1
-        self.M = torch.zeros((self.rows, self.d), dtype=torch.float32)
-        self.mean = np.zeros(self.d)
-        self.unnorm = np.zeros(self.d)
-        self.S = np.zeros(c)
-        self.batch_mean = torch.zeros(self.d, dtype=torch.float64)
-        self.n_seen = self.last_nb = 0
-
-    def batch_rows(self, nb):
-        return self.M[self.c:self.c + nb]
-
-    def step(self, nb):
-        from ganspace_b200 import _native
-        c = self.c
-        X = self.M[c:c + nb].numpy().astype(np.float64)
-        mb = X.mean(0)
-        ss = ((X - mb) ** 2).sum(0)
-        corr = np.sqrt(self.n_seen / (self.n_seen + nb) * nb) * (self.mean - mb) if self.n_seen else np.zeros(self.d)
-        self.M[c:c + nb] = torch.from_numpy((X - mb).astype(np.float32))
-        self.M[c + nb] = torch.from_numpy(corr.astype(np.float32))
-        Mm = self.M[:c + nb + 1].numpy().astype(np.float64)
-        T = torch.from_numpy(Mm @ Mm.T)
-        if self.shard:
-            dist.all_reduce(T)
-        lam, U = np.linalg.eigh(T.numpy())
-        lam, U = lam[::-1][:c], U[:, ::-1][:, :c].T
-        Dn = (U @ Mm).astype(np.float32)
-        idx = np.argmax(np.abs(Dn), axis=1)
-        rowmax = torch.from_numpy(np.stack([np.abs(Dn)[np.arange(c), idx], Dn[np.arange(c), idx]], 1).astype(np.float32))
-        if self.shard:
-            allmax = torch.empty((self.shard[1] * c, 2))
-            dist.all_gather_into_tensor(allmax, rowmax)
-            signs = _native.pick_global_signs(allmax.view(self.shard[1], c, 2)).numpy()
-        else:
-            signs = np.sign(rowmax[:, 1].numpy())
-        self.M[:c] = torch.from_numpy(Dn * signs[:, None])
-        self.S = np.sqrt(lam)
-        if self.n_seen:
-            r = self.n_seen / nb
-            tq = (self.mean * self.n_seen) / r - mb * nb
-            self.unnorm = self.unnorm + ss + r / (self.n_seen + nb) * tq * tq
-        else:
-            self.unnorm = ss
-        self.mean = (self.mean * self.n_seen + mb * nb) / (self.n_seen + nb)
-        self.batch_mean = torch.from_numpy(mb)
-        self.n_seen += nb
-        self.last_nb = nb
-
-    gathered = None      # bound below
-
-    def export(self):
-        out = {"components": (self.M[:self.c] / torch.from_numpy(self.S)[:, None]).float(),
-               "singular_values": torch.from_numpy(self.S.copy()), "mean": torch.from_numpy(self.mean.copy()),
-               "var": torch.from_numpy(self.unnorm / self.n_seen),
-               "explained_variance": torch.from_numpy(self.S ** 2 / (self.n_seen - 1)),
-               "explained_variance_ratio": torch.from_numpy(self.S ** 2 / self.unnorm.sum())}
-        if self.shard:
-            out["components"] = self.gathered(out["components"])
-            out["mean"] = self.gathered(out["mean"].unsqueeze(0)).reshape(-1)
-            out["var"] = self.gathered(out["var"].unsqueeze(0)).reshape(-1)
-            out["explained_variance_ratio"] = out["singular_values"] ** 2 / (out["var"].sum() * self.n_seen)
-        return out
-
-
 def _estimator_worker(rank, world, port, out_path):
     sys.path.insert(0, str(ROOT))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, str(ROOT / "tests"))
+    import fakes                                                       # CPU stand-in engine with BigIPCA's interface
     from ganspace_b200 import _native, estimators
-    _FakeBig.gathered = _native.BigIPCA.gathered                      # the real gather logic (pure torch.distributed)
-    _native.BigIPCA = _FakeBig
+    _native.BigIPCA = fakes.FakeBig
     estimators.DeviceIncrementalPCA.SMALL_D_MAX = 64                  # make d = 256 a "large-d" problem
     d, nb, c, k = 256, 60, 5, 3
     est = estimators.get_estimator("ipca", c, 1.0, device="cpu")
