@@ -181,9 +181,42 @@ class FakeFeatureModel(torch.nn.Module):
         return 1
 
 
+class FakeChain:
+    """Interface of _native.IPCAChain (small-d Gram-form engine); the step is the oracle's Gram-form restatement."""
+
+    def __init__(self, d, c, device, side_stream=True):
+        from oracle import ganspace_oracle as orc
+        self._orc = orc
+        self.d, self.c, self.dev = int(d), int(c), torch.device("cpu")
+        self.st = orc.IPCAState(self.c)
+        self.n_seen = 0
+
+    def step(self, n_batch, mean_b, gram_b):
+        self._orc.ipca_gram_step(self.st, int(n_batch), mean_b.numpy().copy(), gram_b.numpy().copy())
+        self.n_seen += int(n_batch)
+
+    def join(self):
+        pass
+
+    def export(self):
+        st = self.st
+        t = lambda a: torch.from_numpy(np.array(a, dtype=np.float64))
+        return {"components": t(st.components), "singular_values": t(st.singular_values), "mean": t(st.mean), "var": t(st.var),
+                "explained_variance": t(st.explained_variance), "explained_variance_ratio": t(st.explained_variance_ratio)}
+
+
+def fake_batch_stats(x, mean_out=None, gram_out=None):
+    x64 = x.double()
+    mean = x64.mean(0)
+    xc = x64 - mean
+    return mean, xc.T @ xc
+
+
 def install(native, estimators):
     """Swap the device layer of the product for the CPU stand-ins (call inside the process under test)."""
     native.BigIPCA = FakeBig
+    native.IPCAChain = FakeChain
+    native.batch_stats = fake_batch_stats
     native.LinregAccumulator = FakeLinreg
     native.project_std = fake_project_std
     native.require_cuda = lambda device=None: torch.device("cpu")

@@ -21,7 +21,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run_driver():
+SMALL = dict(C=3, H=4, W=4)          # d = 48: the small-d engine, hook read-back, statistics exchange + replay
+
+
+def _run_driver(small=False):
     sys.path.insert(0, str(ROOT / "tests"))
     sys.path.insert(0, str(ROOT))
     import fakes
@@ -29,7 +32,7 @@ def _run_driver():
     from ganspace_b200.config import Config
     from ganspace_b200.netdissect.nethook import InstrumentedModel
     fakes.install(_native, estimators)
-    model = fakes.FakeFeatureModel()
+    model = fakes.FakeFeatureModel(**(SMALL if small else {}))
     inst = InstrumentedModel(model)
     inst.retain_layer("feat")
     cfg = Config(model="Fake", layer="feat", output_class="none", components=C_COMP, n=N, batch_size=B, use_w=False,
@@ -53,19 +56,31 @@ def _check(out, ref, model, oracle):
     assert cmp["lat_mean_rel"] < 1e-5 and np.array_equal(out["lat_stdev"], np.ones(C_COMP, np.float32))
 
 
+_PATCHED = ("BigIPCA", "IPCAChain", "batch_stats", "LinregAccumulator", "project_std", "require_cuda")
+
+
+def test_small_d_driver_single_process(oracle, monkeypatch):
+    """d = 48: generic layer through the retain hook, Gram-form chain, hook-based regression."""
+    from ganspace_b200 import _native
+    for name in _PATCHED:
+        monkeypatch.setattr(_native, name, getattr(_native, name))            # restored after the test
+    out, model = _run_driver(small=True)
+    _check(out, _expected(oracle, model), model, oracle)
+
+
 def test_large_d_driver_single_process(oracle, monkeypatch):
     """d = 2048 > 1024 -> large-d path: producer rows in NHWC order, permutation back to NCHW, native regression."""
     from ganspace_b200 import _native
-    for name in ("BigIPCA", "LinregAccumulator", "project_std", "require_cuda"):
+    for name in _PATCHED:
         monkeypatch.setattr(_native, name, getattr(_native, name))            # restored after the test
     out, model = _run_driver()
     _check(out, _expected(oracle, model), model, oracle)
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, small):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    out, _ = _run_driver()
+    out, _ = _run_driver(small)
     if rank == 0:
         np.savez(out_path, **out)
     dist.barrier()
@@ -76,8 +91,20 @@ def test_large_d_driver_two_ranks_gloo(oracle, tmp_path):
     sys.path.insert(0, str(ROOT / "tests"))
     import fakes
     out_path = str(tmp_path / "driver2.npz")
-    mp.spawn(_worker, args=(2, _free_port(), out_path), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out_path, False), nprocs=2, join=True)
     with np.load(out_path) as data:
         out = {k: data[k] for k in data.files}
     model = fakes.FakeFeatureModel()
+    _check(out, _expected(oracle, model), model, oracle)
+
+
+def test_small_d_driver_two_ranks_gloo(oracle, tmp_path):
+    """Group ownership, ONE all-reduce of the per-group statistics, ordered replay, sharded regression -- at the driver level."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import fakes
+    out_path = str(tmp_path / "driver2s.npz")
+    mp.spawn(_worker, args=(2, _free_port(), out_path, True), nprocs=2, join=True)
+    with np.load(out_path) as data:
+        out = {k: data[k] for k in data.files}
+    model = fakes.FakeFeatureModel(**SMALL)
     _check(out, _expected(oracle, model), model, oracle)
