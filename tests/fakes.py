@@ -181,6 +181,40 @@ class FakeFeatureModel(torch.nn.Module):
         return 1
 
 
+class FakeStyleModel(FakeFeatureModel):
+    """StyleGAN-shaped: a mapping network behind layer 'style', W space via use_w() (wrappers.py:167-179,194-222)."""
+
+    def __init__(self, latent=32, seed=9):
+        super().__init__(C=1, H=1, W=latent, latent=latent, seed=seed)
+        self.model.style = _Identity()
+        g = torch.Generator().manual_seed(seed + 1)
+        self.Mw = torch.randn(latent, latent, generator=g) * (0.7 ** torch.arange(latent, dtype=torch.float32))[:, None]
+        self.w_primary = False
+
+    def use_w(self):
+        self.w_primary = True
+
+    def use_z(self):
+        self.w_primary = False
+
+    def mapping(self, z):
+        return torch.tanh(z @ self.Mw.T) + 0.1 * z
+
+    def latent_space_name(self):
+        return "W" if self.w_primary else "Z"
+
+    def sample_latent(self, n_samples=1, seed=None, truncation=None):
+        z = super().sample_latent(n_samples, seed)
+        return self.mapping(z) if self.w_primary else z
+
+    def partial_forward(self, x, layer_name):
+        assert layer_name == "style"
+        self.model.style(x if self.w_primary else self.mapping(x))
+
+    def feature_layout(self, layer_name):
+        return None
+
+
 class FakeChain:
     """Interface of _native.IPCAChain (small-d Gram-form engine); the step is the oracle's Gram-form restatement."""
 

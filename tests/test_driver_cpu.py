@@ -108,3 +108,63 @@ def test_small_d_driver_two_ranks_gloo(oracle, tmp_path):
         out = {k: data[k] for k in data.files}
     model = fakes.FakeFeatureModel(**SMALL)
     _check(out, _expected(oracle, model), model, oracle)
+
+
+# ---- W space (samples are the latents): the bench configuration's control flow -----------------------------------------
+def _run_style(use_w):
+    sys.path.insert(0, str(ROOT / "tests"))
+    sys.path.insert(0, str(ROOT))
+    import fakes
+    from ganspace_b200 import _native, decomposition, estimators
+    from ganspace_b200.config import Config
+    from ganspace_b200.netdissect.nethook import InstrumentedModel
+    fakes.install(_native, estimators)
+    model = fakes.FakeStyleModel()
+    inst = InstrumentedModel(model)
+    inst.retain_layer("style")
+    cfg = Config(model="FakeStyleGAN", layer="style", output_class="none", components=C_COMP, n=10_000, batch_size=1_000,
+                 use_w=use_w, estimator="ipca")
+    return decomposition.compute_arrays(cfg, inst), model
+
+
+def _expected_style(oracle, model, use_w):
+    normals = lambda seed, b: np.random.RandomState(seed).standard_normal(model.latent * b).reshape(b, model.latent).astype(np.float32)
+    mapping = lambda z: model.mapping(torch.from_numpy(np.ascontiguousarray(z, np.float32))).numpy()
+    if use_w:
+        return oracle.compute_path(lambda s, b: mapping(normals(s, b)), None, model.latent, model.latent, 10_000, 1_000, C_COMP, True,
+                                   use_w=True)
+    return oracle.compute_path(normals, mapping, model.latent, model.latent, 10_000, 1_000, C_COMP, False)
+
+
+def _check_style(out, ref, oracle, use_w):
+    cmp = oracle.compare_npz(out, ref)
+    assert cmp["min_signed_cos"] > 1 - 1e-6 and cmp["max_abs_dvar_ratio"] < 1e-6 and cmp["min_lat_signed_cos"] > 1 - 1e-5, cmp
+    assert cmp["act_mean_rel"] < 1e-5 and cmp["act_stdev_rel"] < 1e-5 and cmp["random_stdevs_rel"] < 1e-4, cmp
+    assert cmp["lat_stdev_rel"] < 1e-4 and cmp["lat_mean_rel"] < 1e-5, cmp
+
+
+def _style_worker(rank, world, port, out_path, use_w):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out, _ = _run_style(use_w)
+    if rank == 0:
+        np.savez(out_path, **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_style_layer_driver_w_and_z_space(oracle, monkeypatch, tmp_path):
+    from ganspace_b200 import _native
+    sys.path.insert(0, str(ROOT / "tests"))
+    import fakes
+    for name in _PATCHED:
+        monkeypatch.setattr(_native, name, getattr(_native, name))
+    for use_w in (True, False):
+        out, model = _run_style(use_w)
+        _check_style(out, _expected_style(oracle, model, use_w), oracle, use_w)
+    # W space on two ranks: the bench configuration's statistics exchange + replay, lat_stdev epilogue
+    out_path = str(tmp_path / "style2.npz")
+    mp.spawn(_style_worker, args=(2, _free_port(), out_path, True), nprocs=2, join=True)
+    with np.load(out_path) as data:
+        out = {k: data[k] for k in data.files}
+    _check_style(out, _expected_style(oracle, fakes.FakeStyleModel(), True), oracle, True)
