@@ -37,6 +37,7 @@ SIGNATURES = {
     "gsb_ipca_chain_step": (_I, [_P, _I, _I, _L, _L, _P, _P, _P, _Z, _P]),
     "gsb_ipca_export": (_I, [_P, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
     "gsb_sym_eig_top": (_I, [_P, _I, _I, _P, _P, _P, _Z, _P]),
+    "gsb_eig_status": (_I, [_P, _P]),
     "gsb_project_std_workspace_bytes": (_Z, [_I]),
     "gsb_project_std": (_I, [_P, _L, _I, _L, _P, _I, _P, _P, _P, _Z, _P]),
     "gsb_linreg_state_bytes": (_Z, [_I, _I]),
@@ -374,9 +375,11 @@ class IPCAChain:
                 _check(lib.gsb_ipca_chain_step(_ptr(self.state), self.d, self.c, self.n_seen, int(n_batch),
                                                _ptr(mean_b), _ptr(gram_b), _ptr(self.ws), self.ws.numel(), _stream()),
                        "gsb_ipca_chain_step")
-        # kernels per step: direct path 8; block-Lanczos path 38 (15 dgemm, chol, trsm, 4 Newton-Schulz, eigensolver, ...)
-        lanczos = self.n_seen > 0 and self.c % 16 == 0 and self.c <= 128 and 3 * self.c <= self.d // 2 + self.d // 8
-        instrument.count(38 if lanczos else 8)
+        # kernels per step: first step = direct solve (8) + seeding of the subspace form (1); later steps = one cluster
+        # launch (orthogonal iteration, csrc/subspace.cu).  Shapes outside the subspace kernel's range: direct solve (8).
+        subspace = (self.d % 128 == 0 and 128 <= self.d <= 512 and self.c % 8 == 0 and 8 <= self.c <= 128
+                    and os.environ.get("GANSPACE_B200_CHAIN", "") not in ("direct", "lanczos"))
+        instrument.count((1 if self.n_seen > 0 else 9) if subspace else 8)
         self.n_seen += int(n_batch)
 
     def join(self):
@@ -400,8 +403,19 @@ class IPCAChain:
                                        _ptr(out["singular_values"]), _ptr(out["mean"]), _ptr(out["var"]),
                                        _ptr(out["explained_variance"]), _ptr(out["explained_variance_ratio"]),
                                        _stream()), "gsb_ipca_export")
+            check_eig_status("IPCAChain.export")
         instrument.count(1)
         return out
+
+
+def check_eig_status(what: str):
+    """Raise if a chain kernel reported a failure since the last check (synchronises the current stream)."""
+    flags = C.c_uint(0)
+    _check(load().gsb_eig_status(C.byref(flags), _stream()), "gsb_eig_status")
+    if flags.value:
+        raise NativeError(f"{what}: a chain step hit its iteration cap without reaching the residual tolerance "
+                          f"(status {flags.value}): the spectrum has no gap after component c; re-run with "
+                          "GANSPACE_B200_CHAIN=direct")
 
 
 def sym_eig_top(a: torch.Tensor, c: int):
@@ -415,6 +429,7 @@ def sym_eig_top(a: torch.Tensor, c: int):
     with torch.cuda.device(a.device):
         _check(lib.gsb_sym_eig_top(_ptr(a), d, c, _ptr(evals), _ptr(evecs), _ptr(ws), ws.numel(), _stream()),
                "gsb_sym_eig_top")
+        check_eig_status("sym_eig_top")
     return evals, evecs
 
 

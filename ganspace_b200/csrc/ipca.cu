@@ -22,18 +22,33 @@
 
 namespace gsb {
 
-constexpr int ST_HDR = 4;   // state header doubles: [0]=n_seen, [1]=steps, [2..3] reserved
+// state header doubles: [0] n_seen, [1] steps, [2] form (0: (V, S) valid; 1: subspace form, (Q, H) authoritative),
+// [3] current Q buffer, [4] iterations of the last subspace step, [5] its relative residual, [6] max residual, [7] total iterations
+constexpr int ST_HDR = 24;   // [8..23]: clocks per phase of the subspace steps (CTA 0), a profiling aid
 
 struct StateView {
     double *hdr, *mean, *unnorm, *S, *V;
+    double *H, *Qbuf;        // subspace form: H[c,c], Q[2][d][c+4] (ping-pong)
+    void *eig_ws;            // workspace of the export-time eigen-decomposition of H
+    size_t bytes;
 };
-__host__ __device__ inline StateView state_view(void *p, int d, int c) {
+static inline size_t export_eig_n(int c) { return (size_t)(c + 31) / 32 * 32; }
+inline StateView state_view(void *p, int d, int c) {
     StateView s;
     s.hdr = reinterpret_cast<double *>(p);
     s.mean = s.hdr + ST_HDR;
     s.unnorm = s.mean + d;
     s.S = s.unnorm + d;
     s.V = s.S + c;
+    size_t off = align_up((size_t)(ST_HDR + 2 * (size_t)d + c + (size_t)c * d) * sizeof(double), 256);
+    s.H = s.Qbuf = nullptr; s.eig_ws = nullptr;
+    if (subspace_applicable(d, c)) {
+        char *b = reinterpret_cast<char *>(p);
+        s.H = reinterpret_cast<double *>(b + off); off += align_up((size_t)c * c * 8, 256);
+        s.Qbuf = reinterpret_cast<double *>(b + off); off += align_up((size_t)2 * d * (c + 4) * 8, 256);
+        s.eig_ws = b + off; off += carve(nullptr, (int)export_eig_n(c), c).bytes;
+    }
+    s.bytes = off;
     return s;
 }
 
@@ -937,6 +952,20 @@ __global__ void export_kernel(const double *hdr, const double *mean, const doubl
 static int eig_top_big(const Workspace &w, int d, int c, double *evals, double *evecs, cudaStream_t st);
 static size_t g_iv_smem_set = 0, g_bis_smem_set = 0;     // largest dynamic-smem opt-in made so far (shared by both paths)
 
+__device__ int g_eig_status = 0;
+int *eig_status_device_ptr() {
+    static int *p = nullptr;
+    if (!p && cudaGetSymbolAddress((void **)&p, g_eig_status) != cudaSuccess) p = nullptr;
+    return p;
+}
+
+int launch_cluster_orth(const double *lam, const double *dg, const double *e, int n, int c, double *Z, cudaStream_t st) {
+    const size_t co_smem = ((size_t)n + c + 64) * sizeof(double) + (size_t)c * sizeof(int);
+    cluster_orth_kernel<<<1, CO_THREADS, co_smem, st>>>(lam, dg, e, n, c, Z);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
 int eig_top(const Workspace &w, int d, int c, double *evals, double *evecs, cudaStream_t st) {
     if (d > 1024) return eig_top_big(w, d, c, evals, evecs, st);
     // Preferred: one 16-CTA cluster (hardware barrier) when the column blocks fit in shared memory.
@@ -1257,6 +1286,12 @@ __global__ void sign_rows_kernel(double *__restrict__ V, int c, int d) {
         for (int i = lane; i < d; i += 32) row[i] = -row[i];
 }
 
+int sign_rows(double *V, int c, int d, cudaStream_t st) {
+    sign_rows_kernel<<<(c + 7) / 8, 256, 0, st>>>(V, c, d);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
 LanczosWs carve_lanczos(void *base, int d, int c) {
     LanczosWs w;
     char *p = reinterpret_cast<char *>(base);
@@ -1277,12 +1312,17 @@ LanczosWs carve_lanczos(void *base, int d, int c) {
     return w;
 }
 bool lanczos_applicable(int d, int c) {
-    static int enabled = -1;
-    if (enabled == -1) {
+    // Round 2: the default chain step is the residual-checked orthogonal iteration of subspace.cu; where it does not apply
+    // the step is the direct solve of the full d x d problem.  The warm-started block-Lanczos step of round 1 (no
+    // convergence check) is an explicit opt-in: GANSPACE_B200_CHAIN=lanczos.
+    static int mode = -1;            // 0 = never, 1 = opted in
+    if (mode == -1) {
         const char *env = getenv("GANSPACE_B200_CHAIN");
-        enabled = (env && strcmp(env, "direct") == 0) ? 0 : 1;
+        mode = (env && strcmp(env, "lanczos") == 0) ? 1 : 0;
     }
-    return enabled && c % 16 == 0 && c <= 128 && 3 * c <= d / 2 + d / 8 && 3 * c <= 512;
+    const bool shapes_ok = c % 16 == 0 && c <= 128 && 3 * c <= d / 2 + d / 8 && 3 * c <= 512;
+    if (mode == 0 || !shapes_ok) return false;
+    return mode == 1;
 }
 
 // orthonormalise the rows of RT[k,d] into out[k,d]: one CholQR pass (Gram, Cholesky, triangular solve) followed
@@ -1356,12 +1396,13 @@ static int check_dims(int d, int c) {
 }  // namespace gsb
 
 extern "C" size_t gsb_ipca_state_bytes(int d, int c) {
-    return (size_t)(gsb::ST_HDR + 2 * (size_t)d + c + (size_t)c * d) * sizeof(double);
+    return gsb::state_view(nullptr, d, c).bytes;
 }
 
 extern "C" size_t gsb_ipca_workspace_bytes(int d, int c) {
     size_t b = gsb::carve(nullptr, d, c).bytes;
     if (gsb::lanczos_applicable(d, c)) b += gsb::carve_lanczos(nullptr, d, c).bytes;
+    if (gsb::subspace_applicable(d, c)) b += gsb::carve_subspace(nullptr, d, c).bytes;
     return b;
 }
 
@@ -1388,6 +1429,19 @@ extern "C" int gsb_ipca_chain_step(void *d_state, int d, int c, int64_t n_seen, 
     }
     cudaStream_t st = (cudaStream_t)stream;
     gsb::StateView s = gsb::state_view(d_state, d, c);
+    const bool subspace = gsb::subspace_applicable(d, c);
+    if (subspace && n_seen > 0) {
+        // steps 2..K: orthogonal iteration on (Q, H), one cluster launch (subspace.cu)
+        size_t off = w.bytes;
+        if (gsb::lanczos_applicable(d, c)) off += gsb::carve_lanczos(nullptr, d, c).bytes;
+        gsb::SubspaceWs sw = gsb::carve_subspace(reinterpret_cast<char *>(d_workspace) + off, d, c);
+        if (workspace_bytes < off + sw.bytes) {
+            gsb::set_error("ipca_chain_step: workspace too small (%zu < %zu)", workspace_bytes, off + sw.bytes);
+            return GSB_ERR_WORKSPACE;
+        }
+        return gsb::subspace_step(s.hdr, s.mean, s.unnorm, s.H, s.Qbuf, d_mean_b, d_gram_b, sw, d, c, (double)n_seen,
+                                  (double)n_batch, st);
+    }
     dim3 grid((d + 31) / 32, (d + 31) / 32), block(32, 8);
     gsb::build_g_kernel<<<grid, block, 0, st>>>(d_gram_b, d_mean_b, s.mean, s.S, s.V, d, c, (double)n_seen,
                                                 (double)n_batch, w.A);
@@ -1407,6 +1461,8 @@ extern "C" int gsb_ipca_chain_step(void *d_state, int d, int c, int64_t n_seen, 
         s.hdr, s.mean, s.unnorm, s.S, s.V, d_mean_b, d_gram_b, w.lam, w.evecs, d, c, (double)n_seen,
         (double)n_batch);
     GSB_CHECK_LAUNCH();
+    // the first step seeds the subspace form: Q = V^T, H = diag(S^2)
+    if (subspace) return gsb::to_subspace_form(s.hdr, s.S, s.V, s.H, s.Qbuf, d, c, st);
     return GSB_OK;
 }
 
@@ -1418,11 +1474,26 @@ extern "C" int gsb_ipca_export(const void *d_state, int d, int c, int64_t n_seen
     if (int r = gsb::check_dims(d, c)) return r;
     GSB_CHECK_ARG(n_seen > 1, "ipca_export: nothing fitted yet");
     gsb::StateView s = gsb::state_view(const_cast<void *>(d_state), d, c);
+    if (gsb::subspace_applicable(d, c)) {
+        // the chain ran on (Q, H): one eigen-decomposition of H gives sklearn's (components_, singular_values_)
+        if (int r = gsb::materialise_components(s.hdr, s.S, s.V, s.H, s.Qbuf, s.eig_ws, d, c, (cudaStream_t)stream)) return r;
+    }
     gsb::export_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(s.hdr, s.mean, s.unnorm, s.S, s.V, d, c,
                                                             (double)n_seen, d_components, d_singular_values,
                                                             d_mean, d_var, d_explained_variance,
                                                             d_explained_variance_ratio);
     GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+extern "C" int gsb_eig_status(unsigned *h_flags, gsb_stream_t stream) {
+    GSB_CHECK_ARG(h_flags, "eig_status: null pointer");
+    int *dp = gsb::eig_status_device_ptr();
+    GSB_CHECK_ARG(dp, "eig_status: no device status word");
+    cudaStream_t st = (cudaStream_t)stream;
+    GSB_CHECK_CUDA(cudaMemcpyAsync(h_flags, dp, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    GSB_CHECK_CUDA(cudaMemsetAsync(dp, 0, sizeof(int), st));
+    GSB_CHECK_CUDA(cudaStreamSynchronize(st));
     return GSB_OK;
 }
 

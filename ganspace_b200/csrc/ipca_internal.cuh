@@ -14,6 +14,26 @@ Workspace carve(void *base, int d, int c);
 // top-c eigenpairs (descending) of the symmetric matrix held in w.A (destroyed); evecs rows are sign-normalised
 int eig_top(const Workspace &w, int d, int c, double *evals, double *evecs, cudaStream_t st);
 
+int launch_cluster_orth(const double *lam, const double *dg, const double *e, int n, int c, double *Z, cudaStream_t st);
+// svd_flip sign rule on the rows of V[c,d]
+int sign_rows(double *V, int c, int d, cudaStream_t st);
+// sticky device-side status word of the chain kernels (bit1: a subspace step hit its iteration cap)
+int *eig_status_device_ptr();
+
+// subspace.cu: chain step as orthogonal iteration on (Q, H) (no per-step eigen-decomposition)
+struct SubspaceWs {
+    double *Gt, *Part, *Red, *Slots;
+    size_t bytes;
+};
+bool subspace_applicable(int d, int c);
+size_t subspace_smem_bytes(int d, int c);
+SubspaceWs carve_subspace(void *base, int d, int c);
+int subspace_step(double *hdr, double *mean, double *unnorm, double *H, double *Qbuf, const double *mean_b, const double *gram_b,
+                  const SubspaceWs &w, int d, int c, double n_seen, double n_b, cudaStream_t st);
+int to_subspace_form(double *hdr, const double *S, const double *V, double *H, double *Qbuf, int d, int c, cudaStream_t st);
+int materialise_components(double *hdr, double *S, double *V, const double *H, const double *Qbuf, void *eig_ws, int d, int c,
+                           cudaStream_t st);
+
 struct LanczosWs {
     double *QbT, *RT, *T, *C, *Linv, *WT, *H, *U, *lamH;
     void *eig_ws;

@@ -108,8 +108,12 @@ int gsb_batch_stats(const float *d_x, int64_t n, int d, int64_t ld, double *d_me
  * Incremental-PCA chain (small-d engine, d <= 1024, d % 32 == 0).
  *   replaces  estimators.py:55-81 IPCAEstimator.fit_partial/get_components, i.e. sklearn
  *   IncrementalPCA.partial_fit: running mean/var merge (extmath.py:1118-1265), rank-c truncated
- *   merge  G = V^T S^2 V + Xc^T Xc + m m^T  -> symmetric eigensolve (Householder tridiagonalisation,
- *   bisection, inverse iteration, back-transform; all fp64, on device) -> top-c -> svd_flip sign rule.
+ *   merge  G = V^T S^2 V + Xc^T Xc + m m^T  -> top-c eigenspace -> svd_flip sign rule; all fp64, on device.
+ *   First step: symmetric eigensolve (Householder tridiagonalisation, bisection, inverse iteration,
+ *   back-transform).  Later steps (d % 128 == 0, d <= 512, c % 8 == 0): the state is kept as an orthonormal
+ *   basis Q of the top-c eigenspace and H = Q^T G Q (V^T S^2 V == Q H Q^T), a step is a residual-checked
+ *   orthogonal iteration on one 16-CTA cluster, and gsb_ipca_export eigen-decomposes H once.  Other shapes
+ *   (or GANSPACE_B200_CHAIN=direct) run the direct eigensolve every step.
  *   The state lives in device memory; chain steps must be enqueued in the reference's batch order.
  * ---------------------------------------------------------------------------------------------- */
 size_t gsb_ipca_state_bytes(int d, int c);
@@ -131,6 +135,13 @@ int gsb_ipca_export(const void *d_state, int d, int c, int64_t n_seen,
  * d <= 1024: cluster / shared-memory tridiagonalisation; 1024 < d <= 4096: L2-resident variant. */
 int gsb_sym_eig_top(double *d_a, int d, int c, double *d_evals, double *d_evecs,
                     void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
+
+/* Sticky status word of the chain kernels (this call synchronises the stream and clears the word):
+ * bit1 = a chain step (orthogonal iteration on the top-c invariant subspace) reached its
+ * iteration cap before its residual tolerance -- the spectrum has no gap after component c; results since the last
+ * call are not trustworthy (re-run with GANSPACE_B200_CHAIN=direct).  Checked by the host wrappers after
+ * gsb_ipca_export / gsb_sym_eig_top. */
+int gsb_eig_status(unsigned *h_flags, gsb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Projection statistics:  out_std[k] = population std over rows r<n of  dirs[k,:] . (x[r,:] - sub[:])
