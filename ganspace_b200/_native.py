@@ -132,10 +132,16 @@ class _Instrument:
         self.launches = 0
         self.timing = False
         self._events = {}
+        self.rows = {}
 
     def reset(self):
         self.launches = 0
         self._events = {}
+        self.rows = {}
+
+    def add_rows(self, name, n):
+        """rows (samples) a section's kernels processed -- the roofline's unit count (bench.py)."""
+        self.rows[name] = self.rows.get(name, 0) + int(n)
 
     def count(self, n):
         self.launches += n
@@ -164,6 +170,19 @@ class _Instrument:
 
 
 instrument = _Instrument()
+
+# the kernels behind each timed section (bench.py's roofline names the one it reports)
+SECTION_KERNELS = {
+    "mapping": "mapping MLP: pixelnorm_split + 8 x mapping_layer_tc_kernel (tcgen05, fp16 hi/lo x3)",
+    "linear": "gen_z linear: sgemm_tn_bias_act_kernel",
+    "synthesis": "StyledConv chain: tap-GEMM tc_gemm_plain (tcgen05) + gather/scatter/blur epilogues",
+}
+
+
+def kernel_name(section: str) -> str:
+    if section == "mapping" and os.environ.get("GANSPACE_B200_MAPPING", MAPPING_DEFAULT) == "simt":
+        return "mapping MLP: pixelnorm + 8 x sgemm_tn_bias_act_kernel (fp32 FMA)"
+    return SECTION_KERNELS.get(section, section)
 
 
 class _Scratch:
@@ -284,6 +303,7 @@ class PackedMapping:
             _check(lib.gsb_mapping_forward(_ptr(self.packed), self.n_layers, self.dim, _ptr(z2), _ptr(out), n,
                                            flags, _ptr(ws), ws.numel(), _stream()), "gsb_mapping_forward")
         instrument.count(self.n_layers + (1 if pixelnorm else 0))
+        instrument.add_rows("mapping", n)
         return out.reshape(z.shape)
 
 
@@ -301,6 +321,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor = None, lrelu: b
         _check(lib.gsb_linear_forward(_ptr(x2), _ptr(w), _ptr(bias.contiguous() if bias is not None else None), _ptr(y),
                                       n, N, K, 1 if lrelu else 0, _ptr(ws), ws.numel(), _stream()), "gsb_linear_forward")
     instrument.count(1)
+    instrument.add_rows("linear", n)
     return y.reshape(*x.shape[:-1], N)
 
 
@@ -552,6 +573,7 @@ class PackedSynthesis:
             chunks = -(-n // max(1, 4096 // (res_in * res_in)))
             launches += 4 + chunks * (3 if self.desc[i].upsample else 2)
         instrument.count(launches)
+        instrument.add_rows("synthesis", n)
         return out
 
     def check(self):
