@@ -31,6 +31,8 @@ SIGNATURES = {
     "gsb_linear_forward": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P, _Z, _P]),
     "gsb_batch_stats_workspace_bytes": (_Z, [_L, _I]),
     "gsb_batch_stats": (_I, [_P, _L, _I, _L, _P, _P, _P, _Z, _P]),
+    "gsb_batch_stats_multi_workspace_bytes": (_Z, [_I, _L, _I]),
+    "gsb_batch_stats_multi": (_I, [_P, _I, _L, _I, _L, _P, _P, _P, _Z, _P]),
     "gsb_ipca_state_bytes": (_Z, [_I, _I]),
     "gsb_ipca_workspace_bytes": (_Z, [_I, _I]),
     "gsb_ipca_reset": (_I, [_P, _I, _I, _P]),
@@ -356,6 +358,25 @@ def batch_stats(x: torch.Tensor, mean_out: torch.Tensor = None, gram_out: torch.
                                    ws.numel(), _stream()), "gsb_batch_stats")
     instrument.count(3)
     return mean_out, gram_out
+
+
+def batch_stats_multi(x: torch.Tensor, n_groups: int, rows_per_group: int, mean_out: torch.Tensor = None,
+                      gram_out: torch.Tensor = None):
+    """(mean[G,d] fp64, centred Gram[G,d,d] fp64) of G consecutive groups of rows of x[G*rows, d] fp32, one set of launches."""
+    lib = load()
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    assert x.shape[0] >= n_groups * rows_per_group
+    d, ld = x.shape[1], x.stride(0)
+    mean = mean_out if mean_out is not None else torch.empty((n_groups, d), dtype=torch.float64, device=x.device)
+    gram = gram_out if gram_out is not None else torch.empty((n_groups, d, d), dtype=torch.float64, device=x.device)
+    assert mean.shape == (n_groups, d) and gram.shape == (n_groups, d, d) and mean.dtype == gram.dtype == torch.float64
+    ws_bytes = lib.gsb_batch_stats_multi_workspace_bytes(n_groups, rows_per_group, d)
+    ws = scratch.get("stats", ws_bytes, x.device)
+    with torch.cuda.device(x.device), instrument.section("stats"):
+        _check(lib.gsb_batch_stats_multi(C.c_void_p(x.data_ptr()), n_groups, rows_per_group, d, ld, _ptr(mean), _ptr(gram),
+                                         _ptr(ws), ws.numel(), _stream()), "gsb_batch_stats_multi")
+    instrument.count(4 if (d % 128 == 0 and d <= 1024) else 3 * n_groups)
+    return mean, gram
 
 
 class IPCAChain:

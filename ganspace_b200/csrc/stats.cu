@@ -118,11 +118,43 @@ gram_centered_kernel(const float *__restrict__ x, int64_t n, int d, int64_t ld, 
         }
 }
 
+// tensor-core form (stats_tc.cu)
+bool stats_tc_supported(int64_t nb, int d);
+size_t stats_tc_workspace_bytes(int n_groups, int64_t nb, int d);
+int stats_tc(const float *x, int n_groups, int64_t nb, int d, int64_t ld, double *mean, double *gram, void *ws, cudaStream_t st);
+
 }  // namespace gsb
 
 extern "C" size_t gsb_batch_stats_workspace_bytes(int64_t n, int d) {
-    (void)n;
+    if (gsb::stats_tc_supported(n, d)) return gsb::stats_tc_workspace_bytes(1, n, d);
     return gsb::align_up((size_t)d * sizeof(double), 256) + gsb::align_up((size_t)d * sizeof(float), 256);
+}
+
+extern "C" size_t gsb_batch_stats_multi_workspace_bytes(int n_groups, int64_t rows_per_group, int d) {
+    if (gsb::stats_tc_supported(rows_per_group, d)) return gsb::stats_tc_workspace_bytes(n_groups, rows_per_group, d);
+    return gsb_batch_stats_workspace_bytes(rows_per_group, d);
+}
+
+// Statistics of n_groups consecutive groups of rows_per_group rows: d_mean [G][d], d_gram [G][d][d].  One set of launches for
+// all groups on the tensor-core path (d % 128 == 0); a loop over the fp32 FMA kernels otherwise.
+extern "C" int gsb_batch_stats_multi(const float *d_x, int n_groups, int64_t rows_per_group, int d, int64_t ld, double *d_mean,
+                                     double *d_gram, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
+    GSB_CHECK_ARG(d_x && d_mean && d_gram && d_workspace, "batch_stats_multi: null pointer");
+    GSB_CHECK_ARG(n_groups > 0 && n_groups <= 65535 && rows_per_group > 0 && d > 0 && d % 4 == 0 && ld >= d && ld % 4 == 0,
+                  "batch_stats_multi: need 0<groups<=65535, rows>0, d%%4==0, ld>=d, ld%%4==0 (groups=%d rows=%lld d=%d ld=%lld)",
+                  n_groups, (long long)rows_per_group, d, (long long)ld);
+    if (workspace_bytes < gsb_batch_stats_multi_workspace_bytes(n_groups, rows_per_group, d)) {
+        gsb::set_error("batch_stats_multi: workspace too small");
+        return GSB_ERR_WORKSPACE;
+    }
+    if (gsb::stats_tc_supported(rows_per_group, d))
+        return gsb::stats_tc(d_x, n_groups, rows_per_group, d, ld, d_mean, d_gram, d_workspace, (cudaStream_t)stream);
+    for (int g = 0; g < n_groups; ++g) {
+        int r = gsb_batch_stats(d_x + (size_t)g * rows_per_group * ld, rows_per_group, d, ld, d_mean + (size_t)g * d,
+                                d_gram + (size_t)g * d * d, d_workspace, workspace_bytes, stream);
+        if (r) return r;
+    }
+    return GSB_OK;
 }
 
 extern "C" int gsb_batch_stats(const float *d_x, int64_t n, int d, int64_t ld, double *d_mean,
@@ -137,6 +169,7 @@ extern "C" int gsb_batch_stats(const float *d_x, int64_t n, int d, int64_t ld, d
         return GSB_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (gsb::stats_tc_supported(n, d)) return gsb::stats_tc(d_x, 1, n, d, ld, d_mean, d_gram, d_workspace, st);
     double *sum = reinterpret_cast<double *>(d_workspace);
     float *mean32 = reinterpret_cast<float *>(reinterpret_cast<char *>(d_workspace) +
                                               gsb::align_up((size_t)d * sizeof(double), 256));

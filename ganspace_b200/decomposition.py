@@ -14,10 +14,10 @@ batch through host memory and runs sklearn's IncrementalPCA on the CPU; here
 so activations never leave HBM; the host only draws the seeds (NumPy global state, as the reference
 does) and receives the final components.
 
-Multi-GPU (one process per GPU, torch.distributed initialised): the partial_fit groups are split into
-contiguous blocks, one per rank; every rank computes the statistics of its groups into slot k of a [K, d*d+d] buffer, ONE
-all-reduce exchanges them, and every rank replays the K-step chain in the reference's order -- the
-result does not depend on the world size.
+Multi-GPU (one process per GPU, torch.distributed initialised): partial_fit group k belongs to rank k mod world; the run
+proceeds in rounds of world x g groups: every rank computes the statistics of its g groups, one all-gather per round hands
+them to every rank, and every rank merges them into its replica of the chain in the reference's order while the next round
+is already being computed -- the result does not depend on the world size.
 """
 from __future__ import annotations
 
@@ -47,6 +47,10 @@ n_clusters = 500
 
 # bytes of latents generated per pipeline chunk (HBM is 180 GB; 8 GiB keeps config 2 in one chunk)
 LATENT_CHUNK_BYTES = 8 << 30
+# partial_fit groups whose statistics are computed by one set of launches (the first block is small so that the merge
+# chain starts early; 10 groups x 10 tile pairs fill the 148 SMs once)
+STATS_FIRST_BLOCK = int(os.environ.get("GANSPACE_B200_STATS_FIRST", 4))
+STATS_BLOCK = int(os.environ.get("GANSPACE_B200_STATS_BLOCK", 10))
 
 
 def get_random_dirs(components, dimensions):
@@ -82,6 +86,34 @@ def _dist():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         return dist.get_rank(), dist.get_world_size(), True
     return 0, 1, False
+
+
+class _StatsExchange:
+    """All-gather of one round's per-group statistics (plan.rounds).  ``start`` enqueues the
+    collective asynchronously; ``finish`` (called one round later, so that the next round's kernels are already queued behind
+    it) merges the round's groups into this rank's chain replica in the reference's group order."""
+
+    def __init__(self, d, world):
+        self.d, self.world = d, world
+
+    def start(self, rnd, means, grams):
+        import torch.distributed as dist
+        g = means.shape[0]
+        recv_m = torch.empty((self.world * g, self.d), dtype=torch.float64, device=means.device)
+        recv_g = torch.empty((self.world * g, self.d, self.d), dtype=torch.float64, device=means.device)
+        works = [dist.all_gather_into_tensor(recv_g, grams, async_op=True),
+                 dist.all_gather_into_tensor(recv_m, means, async_op=True)]
+        return rnd, g, recv_m, recv_g, works, (means, grams)          # the send buffers stay alive until finish()
+
+    def finish(self, pending, transformer, NB):
+        rnd, g, recv_m, recv_g, works, _keep = pending
+        for w in works:
+            w.wait()
+        for kk in rnd:
+            slot = (kk % self.world) * g + (kk - rnd[0]) // self.world
+            if not transformer.fit_partial_stats(NB, recv_m[slot], recv_g[slot]):
+                return False
+        return True
 
 
 def _draw_seeds(count):
@@ -291,37 +323,52 @@ def compute_arrays(config, instrumented_model, state=None):
     K = pl.K
     d = affine.rank if affine is not None else sample_dims
     groups_per_chunk = max(1, int(LATENT_CHUNK_BYTES // max(1, NB * input_dims * 4)))
-    slots = torch.zeros((K, _plan.slot_width(d)), dtype=torch.float64, device=device) if (live and not large_d) else None
     X = None
     tr = transformer.transformer
     state["N"] = N
     k = 0
     stop = False                 # fit_partial returned False (e.g. n_components > first batch): the reference leaves the loop (:262-263)
+    exchange = _StatsExchange(d, world) if (live and not large_d) else None
+
+    def group_rows(rows):
+        """[n, d] activations of the hooked layer for latent rows ``rows`` (small-d engine; n is a multiple of NB)."""
+        if samples_are_latents:
+            return rows
+        if affine is not None:
+            return affine.coords(rows)
+        out = torch.empty((rows.shape[0], d), dtype=torch.float32, device=device)
+        for g0 in range(0, rows.shape[0], NB):
+            for mb in range(0, NB, B):
+                z = rows[g0 + mb:g0 + mb + B].reshape(-1, *input_shape[1:])
+                with torch.no_grad():
+                    model.partial_forward(z, layer_key)
+                batch = inst.retained_features()[layer_key].reshape((z.shape[0], -1))
+                space_left = min(B, NB - mb)
+                out[g0 + mb:g0 + mb + space_left] = batch[:space_left]
+        return out
+
     try:
         for c0 in range(0, K, groups_per_chunk):
             if stop:
                 break
+            c1 = min(c0 + groups_per_chunk, K)
             if large_d:                              # every rank takes part in every group (its row range)
-                mine = list(range(c0, min(c0 + groups_per_chunk, K)))
+                mine = list(range(c0, c1))
             else:
-                mine = _plan.groups_to_process(pl, rank, world, c0, min(c0 + groups_per_chunk, K))
+                mine = _plan.groups_to_process(pl, rank, world, c0, c1)
             runs = _plan.contiguous_runs(mine)
             # every sample_latent call this rank needs for the chunk, generated by ONE launch (one CTA per seed)
             needed, offsets = _plan.batch_slots(pl, runs)
             lat, ensure_rows = _sample_batches_lazy(model, B, [seeds[b] for b in needed])
             lat = lat.reshape(lat.shape[0], -1)
-            for run, off in zip(runs, offsets):
-                if stop:
-                    break
-                for k in run:
-                    r = off + (k - run[0]) * NB
-                    ensure_rows(r + NB)
-                    rows = lat[r:r + NB]
-                    if samples_are_latents:
-                        X = rows
-                    elif affine is not None:
-                        X = affine.coords(rows)
-                    elif large_d:
+            if large_d:
+                for run, off in zip(runs, offsets):
+                    if stop:
+                        break
+                    for k in run:
+                        r = off + (k - run[0]) * NB
+                        ensure_rows(r + NB)
+                        rows = lat[r:r + NB]
                         X = tr.batch_buffer(NB, d, device)              # rows of the engine's stacked matrix, in HBM
                         lo, hi = (rank * (NB // world), (rank + 1) * (NB // world)) if live else (0, NB)   # this rank's rows
                         for mb in range(0, NB, B):
@@ -338,34 +385,57 @@ def compute_arrays(config, instrumented_model, state=None):
                         if not transformer.fit_partial_inplace(NB):
                             stop = True
                             break
-                        continue
-                    else:
-                        X = torch.empty((NB, d), dtype=torch.float32, device=device)
-                        for mb in range(0, NB, B):
-                            z = rows[mb:mb + B].reshape(-1, *input_shape[1:])
-                            with torch.no_grad():
-                                model.partial_forward(z, layer_key)
-                            batch = inst.retained_features()[layer_key].reshape((z.shape[0], -1))
-                            space_left = min(B, NB - mb)
-                            X[mb:mb + space_left] = batch[:space_left]
-                    if live:
-                        if _plan.owner(k, world, K) == rank:
-                            n_b, mean_b, gram_b = tr.batch_stats(X)
-                            slots[k, :d * d] = gram_b.reshape(-1)
-                            slots[k, d * d:] = mean_b
-                    elif not transformer.fit_partial(X):
-                        stop = True
+            else:
+                # small-d engine: rounds of world x g consecutive groups.  The statistics (mean, centred Gram) of this rank's
+                # g groups of a round come out of one set of launches (tensor-core Gram, csrc/stats_tc.cu); the chain steps
+                # follow in the reference's group order, on every rank, from the all-gathered statistics.
+                where = {kk: off + (kk - run[0]) * NB for run, off in zip(runs, offsets) for kk in run}
+                pending = None
+                for rnd in _plan.rounds(c0, c1, world, STATS_FIRST_BLOCK if c0 == 0 else STATS_BLOCK, STATS_BLOCK):
+                    if stop:
                         break
+                    own = [kk for kk in rnd if _plan.owner(kk, world) == rank]
+                    g_max = -(-len(rnd) // world)
+                    means = torch.zeros((g_max, d), dtype=torch.float64, device=device)
+                    grams = torch.zeros((g_max, d, d), dtype=torch.float64, device=device) if (live and len(own) < g_max) \
+                        else torch.empty((g_max, d, d), dtype=torch.float64, device=device)
+                    if own:
+                        k = own[0]
+                        contiguous = all(where[own[i]] == where[own[0]] + i * NB for i in range(len(own)))
+                        spans = [own] if contiguous else [[kk] for kk in own]
+                        i0 = 0
+                        for span in spans:
+                            r0 = where[span[0]]
+                            ensure_rows(r0 + len(span) * NB)
+                            Xb = group_rows(lat[r0:r0 + len(span) * NB])
+                            _native.batch_stats_multi(Xb, len(span), NB, mean_out=means[i0:i0 + len(span)],
+                                                      gram_out=grams[i0:i0 + len(span)])
+                            i0 += len(span)
+                        X = Xb[(len(span) - 1) * NB:]
+                    if (K - 1) in rnd and _plan.owner(K - 1, world) != rank:
+                        r0 = where[K - 1]                                # every rank keeps the final group's sample buffer
+                        ensure_rows(r0 + NB)
+                        X = group_rows(lat[r0:r0 + NB])
+                    if exchange is None:
+                        for i, kk in enumerate(own):
+                            k = kk
+                            if not transformer.fit_partial_stats(NB, means[i], grams[i]):
+                                stop = True
+                                break
+                    else:
+                        cur = exchange.start(rnd, means, grams)
+                        if pending is not None and not exchange.finish(pending, transformer, NB):
+                            stop = True
+                        pending = cur
+                if pending is not None and not stop and not exchange.finish(pending, transformer, NB):
+                    stop = True
             ensure_rows(lat.shape[0])
             del lat    # X (a view of the last group when samples_are_latents) keeps its storage alive
     except KeyboardInterrupt:
         if live:
             raise
-        state["canceled_at"] = int(k) * NB              # the reference's `gi` of the interrupted group (:268-272)
-    if live and not large_d:
-        import torch.distributed as dist
-        dist.all_reduce(slots)                         # the run's single exchange of PCA statistics
-        _plan.replay(pl, slots, d, lambda nb, m, g: tr.merge(nb, m.contiguous(), g.contiguous()))
+        # the reference's `gi` of the interrupted group (:268-272) = the samples merged so far
+        state["canceled_at"] = int(tr.n_samples_seen_)
 
     tick("sampling + activations + IPCA chain")
     X_comp, X_stdev, X_var_ratio = transformer.get_components()

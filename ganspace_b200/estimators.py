@@ -194,6 +194,17 @@ class IPCAEstimator:
             print("\nIPCA error:", e)
             return False
 
+    def fit_partial_stats(self, n_batch, mean_b, gram_b):
+        """fit_partial from the batch's sufficient statistics (n, mean [d], centred Gram [d, d]; fp64 device tensors)
+        instead of its rows -- small-d engine; must be called in the reference's batch order."""
+        try:
+            self.transformer.merge(int(n_batch), mean_b, gram_b)
+            self.transformer.n_samples_seen_ = np.int64(self.transformer.n_samples_seen_)
+            return True
+        except ValueError as e:
+            print("\nIPCA error:", e)
+            return False
+
     def fit_partial_inplace(self, nb):
         """fit_partial on the batch already written into ``transformer.batch_buffer(nb, d, device)`` (large-d engine)."""
         try:

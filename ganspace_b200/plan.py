@@ -1,8 +1,10 @@
 """Host-side batch plan of decomposition.compute and its data-parallel sharding (pure Python, no device).
 
 Restates the reference's sizing rules (decomposition.py:198-232) and defines how the partial_fit groups
-are distributed over ranks: contiguous blocks of groups per rank, statistics exchanged through
-slot k of a [K, d*d+d] buffer with ONE all-reduce, chain replayed in order by every rank.
+are distributed over ranks: group k belongs to rank k mod world; the run proceeds in ROUNDS of
+world x g consecutive groups; in a round every rank computes the statistics (mean, centred Gram) of its g groups with one
+set of launches, one all-gather hands every rank all of the round's statistics, and every rank merges them into its replica
+of the chain in the reference's group order -- while the next round's statistics are already being computed.
 """
 from __future__ import annotations
 
@@ -38,18 +40,29 @@ def make_plan(n: int, B: int, components: int) -> Plan:
     return Plan(B=B, N=N, NB=NB, n_lat=n_lat, K=K)
 
 
-def owner(k: int, world: int, K: int) -> int:
-    """Contiguous block ownership: rank r owns groups [r*ceil(K/world), (r+1)*ceil(K/world)).  Blocks (not
-    k mod world) keep each rank's sample_latent calls contiguous, so they are generated by ONE launch."""
-    per = -(-K // world)
-    return min(world - 1, k // per)
+def owner(k: int, world: int, K: int = 0) -> int:
+    """Round-robin ownership: the chain consumes the groups in order, so with k mod world every rank contributes to every
+    round and the replicated chain can start on group 0 while later groups are still being produced."""
+    return k % world
 
 
 def groups_to_process(plan: Plan, rank: int, world: int, first: int = 0, last: int = None) -> List[int]:
     """Groups a rank touches in [first, last): the ones it owns, plus the final group on every rank (its
     sample buffer feeds random_stdevs, decomposition.py:313-316)."""
     last = plan.K if last is None else last
-    return [k for k in range(first, last) if owner(k, world, plan.K) == rank or k == plan.K - 1]
+    return [k for k in range(first, last) if owner(k, world) == rank or k == plan.K - 1]
+
+
+def rounds(first: int, last: int, world: int, per_rank_first: int, per_rank_later: int) -> List[range]:
+    """Consecutive group ranges covering [first, last): the first round holds world*per_rank_first groups (a small first
+    round lets the merge chain start early), the others world*per_rank_later."""
+    out: List[range] = []
+    a = first
+    while a < last:
+        size = world * (per_rank_first if a == first else per_rank_later)
+        out.append(range(a, min(last, a + max(1, size))))
+        a += max(1, size)
+    return out
 
 
 def contiguous_runs(ks: Sequence[int]) -> List[List[int]]:
@@ -65,12 +78,6 @@ def contiguous_runs(ks: Sequence[int]) -> List[List[int]]:
 def slot_width(d: int) -> int:
     """doubles per statistics slot: centred Gram [d*d] followed by the batch mean [d]."""
     return d * d + d
-
-
-def replay(plan: Plan, slots, d: int, merge: Callable):
-    """Replay the K-step chain from the exchanged statistics, in the reference's group order."""
-    for k in range(plan.K):
-        merge(plan.NB, slots[k, d * d:], slots[k, :d * d].reshape(d, d))
 
 
 def batch_slots(plan: Plan, runs: Sequence[Sequence[int]]):

@@ -103,6 +103,12 @@ int gsb_mapping_status(const void *d_packed, int n_layers, int dim, unsigned *h_
 size_t gsb_batch_stats_workspace_bytes(int64_t n, int d);
 int gsb_batch_stats(const float *d_x, int64_t n, int d, int64_t ld, double *d_mean, double *d_gram,
                     void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
+/* The same for n_groups consecutive groups of rows_per_group rows (the NB-row partial_fit groups of decomposition.py:245-265)
+ * in one set of launches: d_mean [n_groups][d], d_gram [n_groups][d][d].  For d % 128 == 0 (d <= 1024) both entry points
+ * run on the tensor cores (tcgen05, fp16 hi/lo split operands = fp32-grade products, promoted accumulation; stats_tc.cu). */
+size_t gsb_batch_stats_multi_workspace_bytes(int n_groups, int64_t rows_per_group, int d);
+int gsb_batch_stats_multi(const float *d_x, int n_groups, int64_t rows_per_group, int d, int64_t ld, double *d_mean,
+                          double *d_gram, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Incremental-PCA chain (small-d engine, d <= 1024, d % 32 == 0).

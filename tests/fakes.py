@@ -246,11 +246,23 @@ def fake_batch_stats(x, mean_out=None, gram_out=None):
     return mean, xc.T @ xc
 
 
+def fake_batch_stats_multi(x, n_groups, rows_per_group, mean_out=None, gram_out=None):
+    d = x.shape[1]
+    mean = mean_out if mean_out is not None else torch.empty((n_groups, d), dtype=torch.float64)
+    gram = gram_out if gram_out is not None else torch.empty((n_groups, d, d), dtype=torch.float64)
+    for g in range(n_groups):
+        m, G = fake_batch_stats(x[g * rows_per_group:(g + 1) * rows_per_group])
+        mean[g] = m
+        gram[g] = G
+    return mean, gram
+
+
 def install(native, estimators):
     """Swap the device layer of the product for the CPU stand-ins (call inside the process under test)."""
     native.BigIPCA = FakeBig
     native.IPCAChain = FakeChain
     native.batch_stats = fake_batch_stats
+    native.batch_stats_multi = fake_batch_stats_multi
     native.LinregAccumulator = FakeLinreg
     native.project_std = fake_project_std
     native.require_cuda = lambda device=None: torch.device("cpu")

@@ -124,6 +124,14 @@ def test_sharding_partitions_groups():
         assert sorted(sum(owned, [])) == list(range(p.K))
         for r in range(world):
             assert p.K - 1 in plan.groups_to_process(p, r, world)
+        # rounds cover every group once, in order; every rank owns at most ceil(len/world) groups of a round
+        rs = plan.rounds(0, p.K, world, 4, 10)
+        assert [k for r in rs for k in r] == list(range(p.K)) and len(rs[0]) == min(p.K, 4 * world)
+        for rnd in rs:
+            for r in range(world):
+                own = [k for k in rnd if plan.owner(k, world) == r]
+                assert len(own) <= -(-len(rnd) // world)
+                assert [(k - rnd[0]) // world for k in own] == list(range(len(own)))
     assert plan.contiguous_runs([0, 1, 2, 5, 6, 9]) == [[0, 1, 2], [5, 6], [9]]
     # a rank's groups need one contiguous set of sample_latent calls (+ the final group's)
     p2 = plan.make_plan(5_000, 700, 20)          # ragged: B does not divide NB

@@ -1,5 +1,5 @@
-"""world_size-2 gloo test (CPU) of the multi-GPU host logic: group ownership, the slot layout of the
-single statistics all-reduce, and the ordered replay -- with the oracle standing in for the device
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: round-robin group ownership, the per-round
+all-gather of the statistics, and the ordered merge -- with the oracle standing in for the device
 kernels.  The sharded result must equal the single-process chain exactly (it is independent of the
 world size by construction)."""
 import os
@@ -29,26 +29,43 @@ def _groups(seed_base, K, NB, d):
 
 
 def _worker(rank, world, port, out_path):
+    """The protocol of decomposition.compute_arrays' small-d branch: plan.rounds, k mod world ownership, one all-gather of the
+    round's statistics (decomposition._StatsExchange), merges in group order -- the oracle standing in for the device chain."""
     sys.path.insert(0, str(ROOT))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from ganspace_b200 import plan
+    from ganspace_b200 import plan, decomposition
     from oracle import ganspace_oracle as orc
     d, c = 48, 6
     pl = plan.make_plan(n=10_000, B=1_000, components=c)      # N=10000, NB=2000, K=5
     data = _groups(5, pl.K, pl.NB, d)
-    slots = torch.zeros((pl.K, plan.slot_width(d)), dtype=torch.float64)
     touched = plan.groups_to_process(pl, rank, world)
     assert pl.K - 1 in touched
-    for k in touched:
-        if plan.owner(k, world, pl.K) != rank:
-            continue
-        n_b, m, G = orc.batch_stats(data[k])
-        slots[k, :d * d] = torch.from_numpy(G.reshape(-1))
-        slots[k, d * d:] = torch.from_numpy(m)
-    dist.all_reduce(slots)
     st = orc.IPCAState(c)
-    plan.replay(pl, slots.numpy(), d, lambda nb, m, g: orc.ipca_gram_step(st, nb, np.array(m), np.array(g)))
+
+    class Est:                                                 # IPCAEstimator.fit_partial_stats
+        def fit_partial_stats(self, nb, m, g):
+            orc.ipca_gram_step(st, nb, m.numpy().copy(), g.numpy().copy())
+            return True
+
+    ex = decomposition._StatsExchange(d, world)
+    pending, seen = None, []
+    for rnd in plan.rounds(0, pl.K, world, 1, 2):             # rounds of 2, 4, ... groups (ragged last round)
+        own = [k for k in rnd if plan.owner(k, world) == rank]
+        g_max = -(-len(rnd) // world)
+        means = torch.zeros((g_max, d), dtype=torch.float64)
+        grams = torch.zeros((g_max, d, d), dtype=torch.float64)
+        for i, k in enumerate(own):
+            assert k in touched
+            n_b, m, G = orc.batch_stats(data[k])
+            means[i] = torch.from_numpy(m)
+            grams[i] = torch.from_numpy(G)
+        cur = ex.start(rnd, means, grams)
+        if pending is not None:
+            assert ex.finish(pending, Est(), pl.NB)
+        pending = cur
+        seen += list(rnd)
+    assert ex.finish(pending, Est(), pl.NB) and seen == list(range(pl.K))
     if rank == 0:
         np.savez(out_path, comp=st.components, sv=st.singular_values, mean=st.mean, ratio=st.explained_variance_ratio)
     # every rank holds the same state

@@ -56,7 +56,7 @@ def _check(out, ref, model, oracle):
     assert cmp["lat_mean_rel"] < 1e-5 and np.array_equal(out["lat_stdev"], np.ones(C_COMP, np.float32))
 
 
-_PATCHED = ("BigIPCA", "IPCAChain", "batch_stats", "LinregAccumulator", "project_std", "require_cuda")
+_PATCHED = ("BigIPCA", "IPCAChain", "batch_stats", "batch_stats_multi", "LinregAccumulator", "project_std", "require_cuda")
 
 
 def test_small_d_driver_single_process(oracle, monkeypatch):
@@ -99,7 +99,7 @@ def test_large_d_driver_two_ranks_gloo(oracle, tmp_path):
 
 
 def test_small_d_driver_two_ranks_gloo(oracle, tmp_path):
-    """Group ownership, ONE all-reduce of the per-group statistics, ordered replay, sharded regression -- at the driver level."""
+    """Round-robin group ownership, per-round all-gather of the statistics, ordered merge, sharded regression -- at the driver level."""
     sys.path.insert(0, str(ROOT / "tests"))
     import fakes
     out_path = str(tmp_path / "driver2s.npz")

@@ -130,6 +130,30 @@ def test_batch_stats_vs_oracle(nat, oracle, n, d):
     assert np.max(np.abs(g - g_ref)) < 3e-6 * np.max(np.abs(g_ref))
 
 
+@pytest.mark.parametrize("groups,nb,d", [(3, 2000, 512), (5, 777, 256), (2, 10000, 512), (4, 300, 96), (2, 64, 1024)])
+def test_batch_stats_multi_vs_fp64(nat, groups, nb, d):
+    """Several partial_fit groups in one call (tensor-core Gram for d % 128 == 0, fp32 FMA kernels otherwise): every group's
+    statistics against an fp64 evaluation; groups with very different scales exercise the per-group operand exponent."""
+    rng = np.random.RandomState(groups * nb + d)
+    X = (rng.standard_normal((groups * nb, d)) * (1 + rng.rand(d)) + 3 * rng.standard_normal(d)).astype(np.float32)
+    for g in range(groups):
+        X[g * nb:(g + 1) * nb] *= np.float32(10.0 ** (2 * g - 2))
+    xd = torch.tensor(X).cuda()
+    m, G = nat.batch_stats_multi(xd, groups, nb)
+    m, G = m.cpu().numpy(), G.cpu().numpy()
+    for g in range(groups):
+        Xg = X[g * nb:(g + 1) * nb].astype(np.float64)
+        m_ref = Xg.mean(0)
+        Xc = (X[g * nb:(g + 1) * nb] - m_ref.astype(np.float32)).astype(np.float64)     # the kernels centre in fp32
+        G_ref = Xc.T @ Xc
+        assert np.max(np.abs(m[g] - m_ref)) < 1e-12 * max(1, np.max(np.abs(m_ref))) + 1e-13
+        assert np.max(np.abs(G[g] - G[g].T)) == 0.0
+        assert np.max(np.abs(G[g] - G_ref)) < 3e-6 * np.max(np.abs(G_ref)), (g, np.max(np.abs(G[g] - G_ref)) / np.max(np.abs(G_ref)))
+    # a single group through the one-group entry point gives the same numbers
+    m1, G1 = nat.batch_stats(xd[nb:2 * nb])
+    assert np.array_equal(m1.cpu().numpy(), m[1]) and np.array_equal(G1.cpu().numpy(), G[1])
+
+
 @pytest.mark.parametrize("d,c", [(96, 12), (512, 80), (512, 512), (256, 1), (1024, 40)])
 def test_sym_eig_top_vs_lapack(nat, d, c):
     rng = np.random.RandomState(d + c)
