@@ -594,8 +594,10 @@ int subspace_step(double *hdr, double *mean, double *unnorm, double *H, double *
     static int maxit = 0;
     if (tol < 0.0) {
         const char *e1 = getenv("GANSPACE_B200_SUBSPACE_TOL"), *e2 = getenv("GANSPACE_B200_SUBSPACE_MAXIT");
-        tol = e1 ? atof(e1) : 1e-5;
-        if (!(tol > 0.0)) tol = 1e-5;
+        // residual tolerance ||G Q - Q H||_F / min diag H: 1e-4 reproduces the exact chain to cos 0.99999997 over 40 steps of
+        // config 2 (tools/study_subspace_chain.py; 1e-3: 0.999998, 1e-2: 0.99992) with ~25 % fewer iterations than 1e-5
+        tol = e1 ? atof(e1) : 1e-4;
+        if (!(tol > 0.0)) tol = 1e-4;
         maxit = e2 ? atoi(e2) : 60;
         if (maxit < 1) maxit = 60;
     }

@@ -95,15 +95,15 @@ def test_keyboard_interrupt_saves_partial_state(oracle, mapping_weights, monkeyp
     from ganspace_b200.decomposition import get_or_compute
     from ganspace_b200.models import get_instrumented_model, StyleGAN2
     calls = {"n": 0}
-    orig = estimators.IPCAEstimator.fit_partial
+    orig = estimators.IPCAEstimator.fit_partial_stats          # the small-d driver merges groups from their statistics
 
-    def interrupting(self, X):
+    def interrupting(self, *a):
         calls["n"] += 1
         if calls["n"] == 3:
             raise KeyboardInterrupt
-        return orig(self, X)
+        return orig(self, *a)
 
-    monkeypatch.setattr(estimators.IPCAEstimator, "fit_partial", interrupting)
+    monkeypatch.setattr(estimators.IPCAEstimator, "fit_partial_stats", interrupting)
     dev = torch.device("cuda:0")
     model = StyleGAN2(dev, "ffhq", random_init=1234)
     inst = get_instrumented_model("StyleGAN2", "ffhq", "style", dev, model=model, use_w=True)
