@@ -21,9 +21,17 @@
 //     warps 4-7 epilogue      (tcgen05.ld 32x32b -> 2^-s, +bias, leaky-ReLU, *sqrt2 -> split to fp16 hi/lo
 //                              for the next layer, or fp32 for the last layer)
 // smem ring: 2 stages x 96 KB (A_hi 16K, A_lo 16K, W_hi 32K, W_lo 32K), mbarrier full/empty pairs.
+//
+// Round 2: the kernel was L2-bandwidth bound (768 KB of operands per 128 x 256 x 512 tile, two thirds of it weights: 12 GB per
+// layer over 1.01M rows against ~12 TB/s of L2 -> tensor pipe 52 %).  CTAs now run in thread-block clusters of TC_CLUSTER (4)
+// along M: the four CTAs work on four different row tiles and the same weight tile, each loads a quarter of the weight box and
+// TMA-multicasts it into all four shared memories (weight traffic / 4: 6 GB per layer), a stage is recycled when the MMAs of
+// all four CTAs have retired (tcgen05.commit multicast onto every CTA's empty barrier).  A CTA walks through all N tiles of its
+// row tile before moving on, so the second pass over its A rows hits L2.
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace gsb {
 
@@ -37,7 +45,8 @@ constexpr int TC_THREADS = 256;
 constexpr uint32_t TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
 constexpr uint32_t TC_W_BYTES = TC_BLOCK_N * TC_BLOCK_K * 2;   // 32 KB
 constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_W_BYTES;   // 96 KB
-constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t TC_STAGING_BYTES = 2 * TC_A_BYTES + 1024;   // epilogue: two 16 KB output boxes + 256 bias floats
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + TC_STAGING_BYTES;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,6 +77,34 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -127,11 +164,14 @@ struct TcParams {
     const float *inv_wscale;   // device pointer to 2^-s of this layer
     int M, N_total, K;
     int mode;               // 0: (acc 2^-s + bias) -> leaky-ReLU * sqrt2 (EqualLinear);  1: plain acc 2^-s (tc_gemm_plain)
+    int n_groups;           // work units per cluster tile (1 or N_total / 256)
+    int dbg;                // profiling experiments (GANSPACE_B200_MAPPING_DBG): 1 no stores, 2 no W loads, 4 no A loads, 8 no MMAs
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                         const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                        const __grid_constant__ CUtensorMap tm_o0, const __grid_constant__ CUtensorMap tm_o1,
                         const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -145,15 +185,27 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m_tiles = (p.M + TC_BLOCK_M - 1) / TC_BLOCK_M;
     const int num_n_tiles = p.N_total / TC_BLOCK_N;
-    const int num_tiles = num_m_tiles * num_n_tiles;
     const int num_k_blocks = p.K / TC_BLOCK_K;
+    // cluster of cs CTAs along M (cs = 1: no cluster): CTA `crank` of cluster `cluster_id` owns row tile ct * cs + crank of every
+    // cluster tile ct it visits; all CTAs of a cluster run the same number of pipeline steps (row tiles past the end are
+    // zero-filled by the TMA unit and never stored)
+    const uint32_t cs = cluster_nctarank(), crank = cluster_ctarank();
+    const int cluster_id = blockIdx.x / cs, num_clusters = gridDim.x / cs;
+    const int num_ct = (num_m_tiles + (int)cs - 1) / (int)cs;
+    // work unit = (cluster tile, group of consecutive N tiles); n_groups = 1: a CTA walks through all N tiles of its row tile
+    // (its A rows are re-read out of L2), n_groups = num_n_tiles: one output tile per unit (few row tiles: more parallelism)
+    const int n_groups = p.n_groups, tiles_per_group = num_n_tiles / n_groups;
+    const int num_units = num_ct * n_groups;
+    const uint16_t mc_mask = (uint16_t)((1u << cs) - 1u);
+    const uint32_t w_slice_rows = TC_BLOCK_N / cs, w_slice_bytes = TC_W_BYTES / cs;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
         tma_prefetch_desc(&tm_w_hi); tma_prefetch_desc(&tm_w_lo);
+        tma_prefetch_desc(&tm_o0); tma_prefetch_desc(&tm_o1);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], cs); }
         for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -163,6 +215,7 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
     }
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();                    // every CTA's barriers exist before a peer multicasts into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -170,17 +223,31 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / num_n_tiles) * TC_BLOCK_M, n0 = (tile % num_n_tiles) * TC_BLOCK_N;
-                for (int kb = 0; kb < num_k_blocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t *st = smem + stage * TC_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-                    tma_load_2d(&tm_a_hi, &full_bar[stage], st, kb * TC_BLOCK_K, m0);
-                    tma_load_2d(&tm_a_lo, &full_bar[stage], st + TC_A_BYTES, kb * TC_BLOCK_K, m0);
-                    tma_load_2d(&tm_w_hi, &full_bar[stage], st + 2 * TC_A_BYTES, kb * TC_BLOCK_K, n0);
-                    tma_load_2d(&tm_w_lo, &full_bar[stage], st + 2 * TC_A_BYTES + TC_W_BYTES, kb * TC_BLOCK_K, n0);
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            for (int u = cluster_id; u < num_units; u += num_clusters) {
+                const int ct = u / n_groups, ng = u % n_groups;
+                const int m0 = (ct * (int)cs + (int)crank) * TC_BLOCK_M;
+                for (int nt = ng * tiles_per_group; nt < (ng + 1) * tiles_per_group; ++nt) {
+                    const int n0 = nt * TC_BLOCK_N;
+                    for (int kb = 0; kb < num_k_blocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);          // the MMAs of every CTA of the cluster have left this stage
+                        uint8_t *st = smem + stage * TC_STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], ((p.dbg & 4) ? 0u : 2 * TC_A_BYTES) + ((p.dbg & 2) ? 0u : 2 * TC_W_BYTES));
+                        if (!(p.dbg & 4)) {
+                            tma_load_2d(&tm_a_hi, &full_bar[stage], st, kb * TC_BLOCK_K, m0);
+                            tma_load_2d(&tm_a_lo, &full_bar[stage], st + TC_A_BYTES, kb * TC_BLOCK_K, m0);
+                        }
+                        uint8_t *wh = st + 2 * TC_A_BYTES + crank * w_slice_bytes, *wl = wh + TC_W_BYTES;
+                        const int wrow = n0 + (int)(crank * w_slice_rows);
+                        if (p.dbg & 2) {
+                        } else if (cs > 1) {                                      // this CTA's slice of the weight box, to all peers
+                            tma_load_2d_mc(&tm_w_hi, &full_bar[stage], wh, kb * TC_BLOCK_K, wrow, mc_mask);
+                            tma_load_2d_mc(&tm_w_lo, &full_bar[stage], wl, kb * TC_BLOCK_K, wrow, mc_mask);
+                        } else {
+                            tma_load_2d(&tm_w_hi, &full_bar[stage], wh, kb * TC_BLOCK_K, wrow);
+                            tma_load_2d(&tm_w_lo, &full_bar[stage], wl, kb * TC_BLOCK_K, wrow);
+                        }
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -190,7 +257,7 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
             constexpr uint32_t idesc = make_idesc_f16(TC_BLOCK_M, TC_BLOCK_N);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = 0, ntile = ((num_units - cluster_id + num_clusters - 1) / num_clusters) * tiles_per_group; tile < ntile; ++tile) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_BLOCK_N);
@@ -204,12 +271,14 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
                     const uint64_t d_wl = make_sw128_kmajor_desc(st + 2 * TC_A_BYTES + TC_W_BYTES);
 #pragma unroll
                     for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                        if (p.dbg & 8) break;
                         const uint64_t koff = (uint64_t)((k * TC_UMMA_K * 2) >> 4);   // +32 B per K step
                         tc_mma_f16(tmem_d, d_ah + koff, d_wh + koff, idesc, (kb | k) ? 1u : 0u);
                         tc_mma_f16(tmem_d, d_al + koff, d_wh + koff, idesc, 1u);
                         tc_mma_f16(tmem_d, d_ah + koff, d_wl + koff, idesc, 1u);
                     }
-                    tc_commit(&empty_bar[stage]);                 // frees the smem slot when the MMAs retire
+                    if (cs > 1) tc_commit_mc(&empty_bar[stage], mc_mask);   // ... on every CTA of the cluster (their boxes land here too)
+                    else tc_commit(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tfull_bar[acc]);                       // accumulator complete -> epilogue
@@ -217,71 +286,103 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue (TMEM -> registers -> global) =====================
+        // ===================== epilogue (TMEM -> registers -> swizzled smem staging -> TMA store) =====================
+        // Thread = output row.  Row-strided 16-byte global stores cost 6 of the 14.6 ms of the 8-layer network (round-2
+        // experiment: 8.4 ms without them), so the 128 x 64 chunk is staged in shared memory in the SWIZZLE_128B image of the
+        // output box (conflict-free: thread r writes 16-byte piece j of its row to slot j ^ (r & 7)) and one thread hands
+        // it to the TMA unit: full 128-byte lines, rows past M clipped by the tensor map.
         const int ew = warp - 4;                                   // == warp % 4: TMEM lane quadrant
         const int row_in_tile = ew * 32 + lane;
+        const int et = threadIdx.x - 128;                          // 0..127
         const float sqrt2 = 1.41421356237309515f;
         const float inv_wscale = __ldg(p.inv_wscale);
+        uint8_t *stg = smem + TC_STAGES * TC_STAGE_BYTES + 1024;   // [2][16 KB]: (hi, lo) of 64 columns, or 2 x 32 fp32 columns
+        float *bias_s = reinterpret_cast<float *>(stg + 2 * TC_A_BYTES);   // [256]
+        uint8_t *my0 = stg + row_in_tile * 128, *my1 = my0 + TC_A_BYTES;
+        const uint32_t sw = (uint32_t)(row_in_tile & 7);
+        const bool storer = (et == 0);
+        const bool to_f32 = (p.out_f32 != nullptr);
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / num_n_tiles) * TC_BLOCK_M, n0 = (tile % num_n_tiles) * TC_BLOCK_N;
-            const int64_t row = (int64_t)m0 + row_in_tile;
+        bool ovf = false;
+        for (int u = cluster_id; u < num_units; u += num_clusters)
+        for (int nt = (u % n_groups) * tiles_per_group; nt < (u % n_groups + 1) * tiles_per_group; ++nt) {
+            const int m0 = ((u / n_groups) * (int)cs + (int)crank) * TC_BLOCK_M, n0 = nt * TC_BLOCK_N;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TC_BLOCK_N);
-            bool ovf = false;
 #pragma unroll 1
-            for (int c0 = 0; c0 < TC_BLOCK_N; c0 += 32) {
-                uint32_t v[32];
-                tc_ld32(taddr + (uint32_t)c0, v);
+            for (int c0 = 0; c0 < TC_BLOCK_N; c0 += 64) {
+                uint32_t v[64];
+                tc_ld32(taddr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                tc_ld32(taddr + (uint32_t)(c0 + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                 tc_wait_ld();
-                float f[32];
+                if (c0 + 64 == TC_BLOCK_N) {                       // accumulator drained: the MMA warp may refill it
+                    tc_fence_before();
+                    mbar_arrive(&tempty_bar[acc]);
+                }
+                if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging has been read out
+                if (c0 == 0 && p.mode == 0) {                      // (safe: the previous tile's readers passed a barrier below)
+                    bias_s[et] = __ldg(&p.bias[n0 + et]);
+                    bias_s[et + 128] = __ldg(&p.bias[n0 + et + 128]);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                float f[64];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 64; ++j) {
                     float x = __fmul_rn(__uint_as_float(v[j]), inv_wscale);
                     if (p.mode == 0) {
-                        x += __ldg(&p.bias[n0 + c0 + j]);
+                        x += bias_s[c0 + j];
                         x = (x >= 0.f) ? x : __fmul_rn(x, 0.2f);
                         x = __fmul_rn(sqrt2, x);
                     }
                     f[j] = x;
                 }
-                if (row < p.M) {
-                    if (p.out_f32) {
-                        float4 *dst = reinterpret_cast<float4 *>(p.out_f32 + row * p.N_total + n0 + c0);
+                if (to_f32) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    for (int j = 0; j < 8; ++j) {                  // columns [0,32) -> box 0, [32,64) -> box 1; 4 floats per piece
+                        *reinterpret_cast<float4 *>(my0 + (((uint32_t)j ^ sw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        *reinterpret_cast<float4 *>(my1 + (((uint32_t)j ^ sw) << 4)) =
+                            make_float4(f[32 + 4 * j], f[33 + 4 * j], f[34 + 4 * j], f[35 + 4 * j]);
                     }
-                    if (p.out_hi) {
-                        uint32_t hi[16], lo[16];
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            __half h0 = __float2half_rn(f[2 * j]), h1 = __float2half_rn(f[2 * j + 1]);
-                            __half l0 = __float2half_rn(f[2 * j] - __half2float(h0));
-                            __half l1 = __float2half_rn(f[2 * j + 1] - __half2float(h1));
-                            ovf |= (fabsf(f[2 * j]) > 60000.f) | (fabsf(f[2 * j + 1]) > 60000.f);
-                            hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                            lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-                        }
-                        uint4 *dh = reinterpret_cast<uint4 *>(p.out_hi + row * p.N_total + n0 + c0);
-                        uint4 *dl = reinterpret_cast<uint4 *>(p.out_lo + row * p.N_total + n0 + c0);
+                    for (int j = 0; j < 8; ++j) {                  // 8 fp16 per 16-byte piece
+                        uint32_t hi[4], lo[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        for (int q = 0; q < 4; ++q) {
+                            const float a = f[8 * j + 2 * q], b = f[8 * j + 2 * q + 1];
+                            const __half h0 = __float2half_rn(a), h1 = __float2half_rn(b);
+                            const __half l0 = __float2half_rn(a - __half2float(h0)), l1 = __float2half_rn(b - __half2float(h1));
+                            ovf |= (fabsf(a) > 60000.f) | (fabsf(b) > 60000.f);
+                            hi[q] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                            lo[q] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
                         }
+                        *reinterpret_cast<uint4 *>(my0 + (((uint32_t)j ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(my1 + (((uint32_t)j ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the TMA unit
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (storer && !(p.dbg & 1)) {
+                    if (to_f32) {
+                        tma_store_2d(&tm_o0, stg, n0 + c0, m0);
+                        tma_store_2d(&tm_o0, stg + TC_A_BYTES, n0 + c0 + 32, m0);
+                    } else {
+                        tma_store_2d(&tm_o0, stg, n0 + c0, m0);
+                        tma_store_2d(&tm_o1, stg + TC_A_BYTES, n0 + c0, m0);
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             }
-            if (ovf) atomicOr(p.overflow, 1u);
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);                        // 128 arrivals release the accumulator
             if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
+        if (ovf) atomicOr(p.overflow, 1u);
+        if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all output boxes are in global memory
     }
 
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();                    // no CTA leaves while a peer can still signal its barriers
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -393,6 +494,21 @@ static int make_tmap_f16(CUtensorMap *map, const void *base, uint64_t rows, uint
     return GSB_OK;
 }
 
+// 2-D fp32 row-major [rows, cols] tensor, box = 128 rows x 32 columns (128 bytes), 128B swizzle (epilogue output boxes)
+static int make_tmap_f32_out(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return GSB_ERR_CUDA; }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)TC_BLOCK_M};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fp32 output) failed (%d)", (int)r); return GSB_ERR_CUDA; }
+    return GSB_OK;
+}
+
 // Tensor-core packed layout (appended after the fp32 SIMT pack inside the same allocation):
 //   [n_layers][dim*dim] fp16 W_hi | [n_layers][dim*dim] fp16 W_lo | [3][n_layers] float {inv_wscale, wscale, absmax} | flag
 size_t mapping_tc_packed_bytes(int n_layers, int dim) {
@@ -444,6 +560,73 @@ static int tc_ensure_attr() {
     return GSB_OK;
 }
 
+// cluster size of the layer kernel: GANSPACE_B200_MAPPING_CLUSTER = 1 | 2 | 4 (default 4)
+static int tc_cluster_size() {
+    static int cs = 0;
+    if (!cs) {
+        const char *e = getenv("GANSPACE_B200_MAPPING_CLUSTER");
+        cs = e ? atoi(e) : 4;
+        if (cs != 1 && cs != 2 && cs != 4) cs = 4;
+    }
+    return cs;
+}
+
+// clusters of `cs` CTAs that can be resident at once (the kernel is persistent: one wave)
+static int tc_max_clusters(int cs) {
+    static int cache[5] = {0, 0, 0, 0, 0};
+    if (!cache[cs]) {
+        int n = num_sms() / cs;
+        if (cs > 1) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(num_sms() / cs * cs)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int q = 0;
+            if (cudaOccupancyMaxActiveClusters(&q, mapping_layer_tc_kernel, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
+        }
+        cache[cs] = n;
+    }
+    return cache[cs];
+}
+
+// one launch of the layer kernel over `m_tiles` row tiles; W tensor maps must have been built with box rows 256 / cs
+static int tc_launch_layer(const CUtensorMap &tm_ah, const CUtensorMap &tm_al, const CUtensorMap &tm_wh, const CUtensorMap &tm_wl,
+                           TcParams p, int cs, int leave_free_sms, cudaStream_t st) {
+    // output boxes of the epilogue's TMA stores: fp16 hi / lo [M, N] (the next layer's A operand) or fp32 [M, N]
+    CUtensorMap tm_o0, tm_o1;
+    if (p.out_f32) {
+        if (int r = make_tmap_f32_out(&tm_o0, p.out_f32, (uint64_t)p.M, (uint64_t)p.N_total)) return r;
+        tm_o1 = tm_o0;
+    } else {
+        if (int r = make_tmap_f16(&tm_o0, p.out_hi, (uint64_t)p.M, (uint64_t)p.N_total, TC_BLOCK_M)) return r;
+        if (int r = make_tmap_f16(&tm_o1, p.out_lo, (uint64_t)p.M, (uint64_t)p.N_total, TC_BLOCK_M)) return r;
+    }
+    const int m_tiles = (p.M + TC_BLOCK_M - 1) / TC_BLOCK_M, n_tiles = p.N_total / TC_BLOCK_N;
+    const int num_ct = (m_tiles + cs - 1) / cs;
+    int avail = (num_sms() - leave_free_sms) / cs;
+    if (avail < 16 / cs) avail = 16 / cs;
+    const int cap = tc_max_clusters(cs);
+    if (avail > cap) avail = cap;
+    p.n_groups = (num_ct >= 2 * avail) ? 1 : n_tiles;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char *e = getenv("GANSPACE_B200_MAPPING_DBG"); dbg = e ? atoi(e) : 0; }
+        p.dbg = dbg;
+    }
+    const int units = num_ct * p.n_groups;
+    const int clusters = units < avail ? units : avail;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(clusters * cs)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mapping_layer_tc_kernel, tm_ah, tm_al, tm_wh, tm_wl, tm_o0, tm_o1, p));
+    return GSB_OK;
+}
+
 // out[M, N] (fp32, row-major) = (A_hi + A_lo)[M, K] * (W_hi + W_lo)[N, K]^T * inv_wscale   -- the same persistent
 // tcgen05 kernel with the plain epilogue.  Both operands are K-major fp16 hi/lo pairs; K % 64 == 0, N % 256 == 0.
 // Used by the modulated-convolution path (synthesis.cu): one dense contraction per 3x3 tap.
@@ -452,21 +635,18 @@ int tc_gemm_plain(const __half *a_hi, const __half *a_lo, int64_t M, int K, cons
     GSB_CHECK_ARG(N % TC_BLOCK_N == 0 && K % TC_BLOCK_K == 0 && M > 0 && M < (1ll << 31),
                   "tc_gemm_plain: need N%%256==0, K%%64==0 (M=%lld N=%d K=%d)", (long long)M, N, K);
     if (int r = tc_ensure_attr()) return r;
+    // few row tiles (a chunk of a conv layer): no cluster, one output tile per work unit; many: weight multicast
+    const int m_tiles = (int)((M + TC_BLOCK_M - 1) / TC_BLOCK_M);
+    const int cs = (m_tiles >= 4 * num_sms()) ? tc_cluster_size() : 1;
     CUtensorMap tm_ah, tm_al, tm_wh, tm_wl;
     if (int r = make_tmap_f16(&tm_ah, a_hi, (uint64_t)M, (uint64_t)K, TC_BLOCK_M)) return r;
     if (int r = make_tmap_f16(&tm_al, a_lo, (uint64_t)M, (uint64_t)K, TC_BLOCK_M)) return r;
-    if (int r = make_tmap_f16(&tm_wh, w_hi, (uint64_t)N, (uint64_t)K, TC_BLOCK_N)) return r;
-    if (int r = make_tmap_f16(&tm_wl, w_lo, (uint64_t)N, (uint64_t)K, TC_BLOCK_N)) return r;
+    if (int r = make_tmap_f16(&tm_wh, w_hi, (uint64_t)N, (uint64_t)K, TC_BLOCK_N / cs)) return r;
+    if (int r = make_tmap_f16(&tm_wl, w_lo, (uint64_t)N, (uint64_t)K, TC_BLOCK_N / cs)) return r;
     TcParams p;
     p.bias = nullptr; p.out_hi = nullptr; p.out_lo = nullptr; p.out_f32 = out; p.overflow = overflow;
-    p.inv_wscale = inv_wscale; p.M = (int)M; p.N_total = N; p.K = K; p.mode = 1;
-    const int num_tiles = (int)((M + TC_BLOCK_M - 1) / TC_BLOCK_M) * (N / TC_BLOCK_N);
-    int avail = num_sms() - leave_free_sms;
-    if (avail < 16) avail = 16;
-    mapping_layer_tc_kernel<<<num_tiles < avail ? num_tiles : avail, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_ah, tm_al, tm_wh,
-                                                                                                    tm_wl, p);
-    GSB_CHECK_LAUNCH();
-    return GSB_OK;
+    p.inv_wscale = inv_wscale; p.M = (int)M; p.N_total = N; p.K = K; p.mode = 1; p.n_groups = 1;
+    return tc_launch_layer(tm_ah, tm_al, tm_wh, tm_wl, p, cs, leave_free_sms, st);
 }
 
 // Full mapping network on the tensor cores.  ws: 4 fp16 buffers of n*dim (two hi/lo ping-pong pairs).
@@ -484,20 +664,18 @@ int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim,
     pixelnorm_split_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(d_z, a_hi[0], a_lo[0], n, dim, pixelnorm ? 1 : 0,
                                                                   v.overflow);
     GSB_CHECK_LAUNCH();
-    const int num_tiles = (int)((n + TC_BLOCK_M - 1) / TC_BLOCK_M) * (dim / TC_BLOCK_N);
-    // persistent CTAs, one per SM; `leave_free_sms` keeps some SMs idle for a concurrent latency-critical stream
-    // (the IPCA chain's 16-CTA cluster kernels), which otherwise wait for a whole layer launch to drain
-    int avail = num_sms() - leave_free_sms;
-    if (avail < 16) avail = 16;
-    const int grid = num_tiles < avail ? num_tiles : avail;
+    // persistent CTAs in clusters, one CTA per SM; `leave_free_sms` keeps some SMs idle for a concurrent latency-critical
+    // stream (the IPCA chain's 16-CTA cluster kernels), which otherwise wait for a whole layer launch to drain
+    const int m_tiles = (int)((n + TC_BLOCK_M - 1) / TC_BLOCK_M);
+    const int cs = (m_tiles >= 64) ? tc_cluster_size() : 1;
     const int64_t per = (int64_t)dim * dim;
     for (int l = 0; l < n_layers; ++l) {
         const int src = l & 1, dst = src ^ 1;
         CUtensorMap tm_ah, tm_al, tm_wh, tm_wl;
         if (int r = make_tmap_f16(&tm_ah, a_hi[src], (uint64_t)n, dim, TC_BLOCK_M)) return r;
         if (int r = make_tmap_f16(&tm_al, a_lo[src], (uint64_t)n, dim, TC_BLOCK_M)) return r;
-        if (int r = make_tmap_f16(&tm_wh, v.w_hi + l * per, dim, dim, TC_BLOCK_N)) return r;
-        if (int r = make_tmap_f16(&tm_wl, v.w_lo + l * per, dim, dim, TC_BLOCK_N)) return r;
+        if (int r = make_tmap_f16(&tm_wh, v.w_hi + l * per, dim, dim, TC_BLOCK_N / cs)) return r;
+        if (int r = make_tmap_f16(&tm_wl, v.w_lo + l * per, dim, dim, TC_BLOCK_N / cs)) return r;
         TcParams p;
         p.bias = pb + (int64_t)l * dim;
         const bool last = (l == n_layers - 1);
@@ -506,9 +684,8 @@ int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim,
         p.out_f32 = last ? d_w : nullptr;
         p.overflow = v.overflow;
         p.inv_wscale = v.inv_wscale + l;
-        p.M = (int)n; p.N_total = dim; p.K = dim; p.mode = 0;
-        mapping_layer_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_ah, tm_al, tm_wh, tm_wl, p);
-        GSB_CHECK_LAUNCH();
+        p.M = (int)n; p.N_total = dim; p.K = dim; p.mode = 0; p.n_groups = 1;
+        if (int r = tc_launch_layer(tm_ah, tm_al, tm_wh, tm_wl, p, cs, leave_free_sms, st)) return r;
     }
     return GSB_OK;
 }
