@@ -47,6 +47,9 @@ SIGNATURES = {
     "gsb_linreg_workspace_bytes": (_Z, [_L, _I]),
     "gsb_linreg_accumulate": (_I, [_P, _I, _I, _P, _L, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "gsb_linreg_solve": (_I, [_P, _I, _I, _L, _P, _P, _P]),
+    "gsb_linreg_solve_status": (_I, [_P, _I, _I, _P, _P]),
+    "gsb_linreg_normal_matrix": (_P, [_P, _I, _I]),
+    "gsb_linreg_solve_pinv": (_I, [_P, _I, _I, _P, _P, _D, _P, _P]),
     "gsb_synthesis_packed_bytes": (_Z, [_P, _I, _I]),
     "gsb_synthesis_pack": (_I, [_P, _I, _I, _P, _P, _Z, _P]),
     "gsb_synthesis_workspace_bytes": (_Z, [_P, _I, _L]),
@@ -518,14 +521,39 @@ class LinregAccumulator:
         instrument.count(2)
         self.n_total += n
 
+    RCOND = 1e-6        # eigenvalues of A^T A below RCOND * largest count as zero in the minimum-norm fallback
+
     def solve(self):
+        """(M_t [c, L], Z_mean [L]) fp64.  Well-conditioned normal equations (the usual case: the columns of A are unit-variance
+        PC coordinates) are solved by Cholesky; if a pivot fails, the minimum-norm least-squares solution is formed from the
+        eigen-decomposition of A^T A -- what scipy's gelsd (decomposition.py:133) returns for a rank-deficient A."""
         lib = load()
-        M = torch.empty((self.c, self.L), dtype=torch.float64, device=self.dev)
+        M = torch.zeros((self.c, self.L), dtype=torch.float64, device=self.dev)
         zmean = torch.empty(self.L, dtype=torch.float64, device=self.dev)
+        info = C.c_int(0)
         with torch.cuda.device(self.dev):
             _check(lib.gsb_linreg_solve(_ptr(self.state), self.c, self.L, self.n_total, _ptr(M), _ptr(zmean), _stream()),
                    "gsb_linreg_solve")
+            _check(lib.gsb_linreg_solve_status(_ptr(self.state), self.c, self.L, C.byref(info), _stream()), "gsb_linreg_solve_status")
         instrument.count(1)
+        self.rank_deficient_at = int(info.value)
+        if info.value != 0:
+            n = (self.c + 31) // 32 * 32                      # the eigensolver wants a multiple of 32: pad with a -1 diagonal
+            off = int(lib.gsb_linreg_normal_matrix(_ptr(self.state), self.c, self.L)) - self.state.data_ptr()
+            ata = self.state[off:off + self.c * self.c * 8].view(torch.float64).view(self.c, self.c)
+            if not bool(torch.isfinite(ata).all()):
+                raise NativeError("latent regression: the normal equations contain non-finite entries (a zero or NaN stdev "
+                                  "column?); scipy's lstsq raises on such input as well")
+            pad = torch.zeros((n, n), dtype=torch.float64, device=self.dev)
+            pad[:self.c, :self.c] = ata
+            if n > self.c:
+                pad[self.c:, self.c:] = -torch.eye(n - self.c, dtype=torch.float64, device=self.dev)
+            evals, evecs = sym_eig_top(pad, self.c)           # padding eigenvalues (-1) sort last and are not returned
+            evecs = evecs[:, :self.c].contiguous()
+            with torch.cuda.device(self.dev):
+                _check(lib.gsb_linreg_solve_pinv(_ptr(self.state), self.c, self.L, _ptr(evals), _ptr(evecs), self.RCOND, _ptr(M),
+                                                 _stream()), "gsb_linreg_solve_pinv")
+            instrument.count(9)
         return M, zmean
 
 

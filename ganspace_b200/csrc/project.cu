@@ -158,17 +158,38 @@ linreg_normal_eq_kernel(const float *__restrict__ A, const float *__restrict__ Z
     }
 }
 
-// single-CTA Cholesky solve  M = AtA^-1 AtZ  (c <= 512), fp64; AtA is overwritten by its factor
+// single-CTA Cholesky solve  M = AtA^-1 AtZ  (c <= 512), fp64, on a copy of AtA (`fac`).  A pivot that is not clearly
+// positive (<= 1e-6 of the largest diagonal entry: the columns of A are numerically dependent, or hold NaN) sets info = k + 1
+// and zeroes M; the caller then takes the minimum-norm route (linreg_pinv_kernel), which is what the reference's
+// scipy.linalg.lstsq(..., lapack_driver='gelsd') returns for a rank-deficient A (decomposition.py:133).
 __global__ void __launch_bounds__(1024)
-linreg_solve_kernel(double *__restrict__ AtA, const double *__restrict__ AtZ, const double *__restrict__ sumZ,
-                    int c, int L, double n_total, double *__restrict__ M, double *__restrict__ zmean,
-                    int *__restrict__ info) {
+linreg_solve_kernel(const double *__restrict__ AtA_in, double *__restrict__ AtA, const double *__restrict__ AtZ,
+                    const double *__restrict__ sumZ, int c, int L, double n_total, double *__restrict__ M,
+                    double *__restrict__ zmean, int *__restrict__ info) {
     const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ double red[64];
+    double dmax = 0.0;
+    for (int i = tid; i < c * c; i += nt) {
+        const double v = AtA_in[i];
+        AtA[i] = v;
+        if (i / c == i % c) dmax = fmax(dmax, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    if ((tid & 31) == 0) red[tid >> 5] = dmax;
+    __syncthreads();
+    dmax = 0.0;
+    for (int q = 0; q < (nt >> 5); ++q) dmax = fmax(dmax, red[q]);
+    const double floor_ = 1e-6 * dmax;
+    for (int col = tid; col < L; col += nt) zmean[col] = sumZ[col] / n_total;
     // right-looking Cholesky, lower factor stored in AtA
     for (int k = 0; k < c; ++k) {
         __syncthreads();
         double dkk = AtA[(size_t)k * c + k];
-        if (!(dkk > 0.0)) { if (tid == 0) *info = k + 1; return; }
+        if (!(dkk > floor_)) {
+            if (tid == 0) *info = k + 1;
+            for (int i = tid; i < c * L; i += nt) M[i] = 0.0;
+            return;
+        }
         double lkk = sqrt(dkk);
         __syncthreads();
         for (int i = k + tid; i < c; i += nt) AtA[(size_t)i * c + k] = (i == k) ? lkk : AtA[(size_t)i * c + k] / lkk;
@@ -191,12 +212,31 @@ linreg_solve_kernel(double *__restrict__ AtA, const double *__restrict__ AtZ, co
             for (int k = i + 1; k < c; ++k) s -= AtA[(size_t)k * c + i] * M[(size_t)k * L + col];
             M[(size_t)i * L + col] = s / AtA[(size_t)i * c + i];
         }
-        zmean[col] = sumZ[col] / n_total;
     }
     if (tid == 0) *info = 0;
 }
 
-struct LinregView { double *AtA, *AtZ, *sumZ; int *info; size_t bytes; };
+// Minimum-norm least squares from the eigen-decomposition AtA = sum_i lam_i v_i v_i^T:  M = sum_{lam_i > rcond lam_max}
+// v_i (v_i^T AtZ) / lam_i.   evecs[c][c]: rows are eigenvectors (descending eigenvalues).  grid.x = L columns in chunks of 128.
+__global__ void __launch_bounds__(128)
+linreg_pinv_kernel(const double *__restrict__ lam, const double *__restrict__ evecs, const double *__restrict__ AtZ, int c, int L,
+                   double rcond, double *__restrict__ M) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= L) return;
+    const double cut = rcond * fmax(lam[0], 0.0);
+    for (int i = 0; i < c; ++i) M[(size_t)i * L + col] = 0.0;
+    for (int t = 0; t < c; ++t) {
+        const double l = lam[t];
+        if (!(l > cut)) continue;
+        const double *v = evecs + (size_t)t * c;
+        double proj = 0.0;
+        for (int k = 0; k < c; ++k) proj = fma(v[k], AtZ[(size_t)k * L + col], proj);
+        proj /= l;
+        for (int i = 0; i < c; ++i) M[(size_t)i * L + col] = fma(v[i], proj, M[(size_t)i * L + col]);
+    }
+}
+
+struct LinregView { double *AtA, *AtZ, *sumZ, *fac; int *info; size_t bytes; };
 static LinregView linreg_view(void *p, int c, int L) {
     LinregView v;
     char *b = reinterpret_cast<char *>(p);
@@ -205,6 +245,7 @@ static LinregView linreg_view(void *p, int c, int L) {
     v.AtZ = (double *)(b + off); off += align_up((size_t)c * L * 8, 256);
     v.sumZ = (double *)(b + off); off += align_up((size_t)L * 8, 256);
     v.info = (int *)(b + off); off += 256;
+    v.fac = (double *)(b + off); off += align_up((size_t)c * c * 8, 256);
     v.bytes = off;
     return v;
 }
@@ -276,8 +317,34 @@ extern "C" int gsb_linreg_solve(void *d_state, int c, int latent_dim, int64_t n_
                                 double *d_z_mean, gsb_stream_t stream) {
     GSB_CHECK_ARG(d_state && d_M_t && d_z_mean && c > 0 && c <= 512 && n_total > 0, "linreg_solve: bad arguments");
     gsb::LinregView v = gsb::linreg_view(d_state, c, latent_dim);
-    gsb::linreg_solve_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(v.AtA, v.AtZ, v.sumZ, c, latent_dim,
+    gsb::linreg_solve_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(v.AtA, v.fac, v.AtZ, v.sumZ, c, latent_dim,
                                                                   (double)n_total, d_M_t, d_z_mean, v.info);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+// 0 = the Cholesky solve succeeded; k > 0 = pivot k was not positive (rank-deficient / non-finite normal equations): M was
+// zeroed, call gsb_linreg_solve_pinv.  Synchronises the stream.
+extern "C" int gsb_linreg_solve_status(const void *d_state, int c, int latent_dim, int *h_info, gsb_stream_t stream) {
+    GSB_CHECK_ARG(d_state && h_info && c > 0 && latent_dim > 0, "linreg_solve_status: bad arguments");
+    gsb::LinregView v = gsb::linreg_view(const_cast<void *>(d_state), c, latent_dim);
+    GSB_CHECK_CUDA(cudaMemcpyAsync(h_info, v.info, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    GSB_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return GSB_OK;
+}
+
+extern "C" const double *gsb_linreg_normal_matrix(const void *d_state, int c, int latent_dim) {
+    return gsb::linreg_view(const_cast<void *>(d_state), c, latent_dim).AtA;
+}
+
+// Minimum-norm solution from the eigenpairs of the normal matrix (gsb_sym_eig_top of gsb_linreg_normal_matrix, all c of them):
+// eigenvalues <= rcond * largest are dropped, as gelsd drops small singular values.
+extern "C" int gsb_linreg_solve_pinv(const void *d_state, int c, int latent_dim, const double *d_evals, const double *d_evecs,
+                                     double rcond, double *d_M_t, gsb_stream_t stream) {
+    GSB_CHECK_ARG(d_state && d_evals && d_evecs && d_M_t && c > 0 && c <= 512 && rcond >= 0.0, "linreg_solve_pinv: bad arguments");
+    gsb::LinregView v = gsb::linreg_view(const_cast<void *>(d_state), c, latent_dim);
+    gsb::linreg_pinv_kernel<<<(latent_dim + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_evals, d_evecs, v.AtZ, c, latent_dim, rcond,
+                                                                                     d_M_t);
     GSB_CHECK_LAUNCH();
     return GSB_OK;
 }

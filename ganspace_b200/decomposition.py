@@ -318,6 +318,12 @@ def compute_arrays(config, instrumented_model, state=None):
 
     # ---- Phase A: the seeds of every sample_latent(B) call the reference makes (:232-236) ----------
     seeds = _draw_seeds(pl.n_calls)
+    # W-space runs end with model.sample_latent(5000) for lat_stdev (:325-329).  Without a regression pass nothing touches the
+    # global NumPy state in between, so its seed is the next draw; its latent stream (one sequential MT19937 stream, ~6 ms on
+    # one SM) is generated on a side stream while the run proceeds instead of at the tail of the critical path.
+    lat_stdev_z = None
+    if config.use_w and samples_are_latents and hasattr(model, "draw_z_async"):
+        lat_stdev_z = model.draw_z_async(5000, _draw_seeds(1)[0])
 
     # ---- Phase B: per-group statistics + merge chain (:239-265) ------------------------------------
     K = pl.K
@@ -492,7 +498,10 @@ def compute_arrays(config, instrumented_model, state=None):
 
     lat_stdev = np.ones_like(X_stdev)
     if config.use_w:
-        samples = model.sample_latent(5000).reshape(5000, input_dims)
+        if lat_stdev_z is not None:
+            samples = model.z_to_latent(lat_stdev_z()).reshape(5000, input_dims)
+        else:
+            samples = model.sample_latent(5000).reshape(5000, input_dims)
         zc = torch.from_numpy(Z_comp.reshape(-1, input_dims).astype(np.float32))
         lat_stdev = _native.project_std(samples.contiguous(), zc).cpu().numpy()
 

@@ -151,6 +151,29 @@ class StyleGAN2(BaseModel):
             z = self.model.style(z)
         return z
 
+    def draw_z_async(self, n_samples, seed):
+        """The Z stream of ``sample_latent(n_samples, seed=seed)`` generated on a side stream; returns a callable that makes
+        the current stream wait for it and hands back z [n_samples, 512]."""
+        side = getattr(self, "_side_stream", None)
+        if side is None:
+            with torch.cuda.device(self.device):
+                side = self._side_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.device(self.device):
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                z = _native.legacy_normal([seed], 512 * n_samples, self.device).view(n_samples, 512)
+
+        def result():
+            with torch.cuda.device(self.device):
+                torch.cuda.current_stream().wait_stream(side)
+            z.record_stream(torch.cuda.current_stream())
+            return z
+        return result
+
+    def z_to_latent(self, z):
+        """What sample_latent does after drawing z (wrappers.py:176-179): the mapping network in W mode."""
+        return self.model.style(z) if self.w_primary else z
+
     def sample_latents_multi(self, n_samples, seeds, out=None, lazy=False):
         """Several ``sample_latent(n_samples, seed=s)`` calls in ONE launch (one CTA per seed);
         ``out`` is an optional [len(seeds)*n_samples, 512] device buffer.  Used by the decomposition

@@ -176,6 +176,14 @@ int gsb_linreg_accumulate(void *d_state, int c, int latent_dim, const float *d_a
 size_t gsb_linreg_workspace_bytes(int64_t n, int c);
 int gsb_linreg_solve(void *d_state, int c, int latent_dim, int64_t n_total, double *d_M_t,
                      double *d_z_mean, gsb_stream_t stream);
+/* Rank-deficient / ill-conditioned normal equations (the reference's gelsd returns the minimum-norm solution there,
+ * decomposition.py:133): gsb_linreg_solve checks its Cholesky pivots against 1e-6 of the largest diagonal entry; on failure it
+ * zeroes d_M_t and records the pivot.  gsb_linreg_solve_status reads that record (0 = fine; synchronises).  The caller then
+ * eigen-decomposes gsb_linreg_normal_matrix (c x c, fp64, device) with gsb_sym_eig_top and calls gsb_linreg_solve_pinv. */
+int gsb_linreg_solve_status(const void *d_state, int c, int latent_dim, int *h_info, gsb_stream_t stream);
+const double *gsb_linreg_normal_matrix(const void *d_state, int c, int latent_dim);
+int gsb_linreg_solve_pinv(const void *d_state, int c, int latent_dim, const double *d_evals, const double *d_evecs, double rcond,
+                          double *d_M_t, gsb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * StyleGAN2 synthesis up to a hooked StyledConv (layer = conv1 | convs.k; BASELINE config 5 family)

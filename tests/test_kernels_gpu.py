@@ -241,6 +241,30 @@ def test_linreg_accumulate_solve(nat):
     assert np.allclose(zmean.cpu().numpy(), Z.mean(axis=0), atol=1e-6)
 
 
+def test_linreg_rank_deficient_matches_gelsd_min_norm(nat):
+    """Two identical projection directions make A rank-deficient: the reference's gelsd (decomposition.py:133) returns the
+    minimum-norm solution; the Cholesky route must notice and the eigen route must reproduce it."""
+    import scipy.linalg
+    rng = np.random.RandomState(10)
+    n, d, c, L = 2000, 256, 12, 128
+    act = rng.standard_normal((n, d)).astype(np.float32)
+    comp = np.ascontiguousarray(np.linalg.qr(rng.standard_normal((d, c)))[0].T.astype(np.float32))
+    comp[7] = comp[3]                                         # duplicated component -> duplicated column of A
+    mean = rng.standard_normal(d).astype(np.float32)
+    stdev = np.ones(c, np.float32)
+    Z = rng.standard_normal((n, L)).astype(np.float32)
+    A = ((act - mean) @ comp.T) / stdev
+    M_ref = scipy.linalg.lstsq(A.astype(np.float64), Z.astype(np.float64), lapack_driver="gelsd", cond=1e-4)[0]
+    acc = nat.LinregAccumulator(c, L, "cuda")
+    acc.accumulate(torch.tensor(act).cuda(), torch.tensor(comp).cuda(), torch.tensor(mean).cuda(), torch.tensor(stdev).cuda(),
+                   torch.tensor(Z).cuda())
+    M, zmean = acc.solve()
+    M = M.cpu().numpy()
+    assert acc.rank_deficient_at > 0
+    assert np.all(np.isfinite(M)) and np.max(np.abs(M - M_ref)) < 1e-4, np.max(np.abs(M - M_ref))
+    assert np.max(np.abs(M[3] - M[7])) < 1e-6                 # minimum norm: the duplicated columns share the weight equally
+
+
 def test_estimator_accepts_host_arrays_and_cuda_tensors(golden):
     """IPCAEstimator keeps the reference's ndarray interface (estimators.py:68-81) and takes CUDA tensors as is."""
     from ganspace_b200.estimators import get_estimator
