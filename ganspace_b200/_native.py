@@ -23,6 +23,12 @@ SIGNATURES = {
     "gsb_legacy_normal_f32": (_I, [_P, _I, _L, _P, _L, _P]),
     "gsb_legacy_truncnorm_f32": (_I, [_P, _I, _L, _D, _D, _F, _P, _L, _P]),
     "gsb_mt19937_raw_u32": (_I, [_P, _I, _L, _P, _L, _P]),
+    "gsb_mt19937_jump_polys": (_I, [_L, _I, _P]),
+    "gsb_mt19937_jump_state_host": (_I, [C.c_uint32, _P, _P]),
+    "gsb_legacy_normal_split_step_words": (_L, [_L, _I]),
+    "gsb_legacy_normal_split_workspace_bytes": (_Z, [_I, _L, _I]),
+    "gsb_legacy_normal_f32_split": (_I, [_P, _I, _L, _P, _L, _I, _P, _P, _Z, _P]),
+    "gsb_legacy_normal_split_status": (_I, [_P, _I, _L, _I, _P, _P]),
     "gsb_mapping_packed_bytes": (_Z, [_I, _I]),
     "gsb_mapping_pack": (_I, [_P, _P, _I, _I, _F, _P, _P]),
     "gsb_mapping_workspace_bytes": (_Z, [_L, _I]),
@@ -214,8 +220,39 @@ scratch = _Scratch()
 # ------------------------------------------------------------------------------------------------
 # thin tensor-level wrappers
 # ------------------------------------------------------------------------------------------------
-def legacy_normal(seeds, n_per_stream: int, device, out=None) -> torch.Tensor:
-    """RandomState(seed).standard_normal(n_per_stream).astype(float32) for every seed -> [S, n]."""
+_jump_polys = {}        # (step_words, count) -> host table; (step_words, count, device) -> device copy
+
+
+def jump_polys(n_per_stream: int, parts: int, device) -> torch.Tensor:
+    """Device copy of the MT19937 jump polynomials for streams of n_per_stream normals split into `parts` sub-streams
+    (computed once per process on the host, ~0.1 s; csrc/rng_jump.cu)."""
+    import numpy as np
+    lib = load()
+    step = int(lib.gsb_legacy_normal_split_step_words(int(n_per_stream), int(parts)))
+    key = (step, parts - 1)
+    if key not in _jump_polys:
+        table = np.zeros((parts - 1, 624), np.uint32)
+        _check(lib.gsb_mt19937_jump_polys(step, parts - 1, table.ctypes.data_as(C.c_void_p)), "gsb_mt19937_jump_polys")
+        _jump_polys[key] = table
+    dkey = key + (str(device),)
+    if dkey not in _jump_polys:
+        _jump_polys[dkey] = torch.from_numpy(_jump_polys[key].view(np.int32)).to(device)
+    return _jump_polys[dkey]
+
+
+def split_parts(n_per_stream: int) -> int:
+    """CTAs per stream: long streams (a 10k-row batch = 5.12M normals = 8.6 ms on one SM) are generated by up to 8 CTAs."""
+    env = os.environ.get("GANSPACE_B200_RNG_PARTS")
+    if env:
+        return max(1, min(16, int(env)))
+    if n_per_stream % 2:
+        return 1
+    return max(1, min(8, n_per_stream // 600_000))
+
+
+def legacy_normal(seeds, n_per_stream: int, device, out=None, parts: int = 1) -> torch.Tensor:
+    """RandomState(seed).standard_normal(n_per_stream).astype(float32) for every seed -> [S, n].
+    ``parts`` > 1: every stream is generated by that many CTAs (MT19937 jump-ahead), bit-identical output."""
     lib = load()
     dev = require_cuda(device)
     seeds_dev = _seeds_tensor(seeds, dev)
@@ -223,6 +260,14 @@ def legacy_normal(seeds, n_per_stream: int, device, out=None) -> torch.Tensor:
     if out is None:
         out = torch.empty((S, n_per_stream), dtype=torch.float32, device=dev)
     assert out.is_cuda and out.is_contiguous() and out.numel() >= S * n_per_stream
+    if parts > 1 and S > 0 and n_per_stream >= 2 and n_per_stream % 2 == 0:
+        polys = jump_polys(n_per_stream, parts, dev)
+        ws = scratch.get("rng_split", lib.gsb_legacy_normal_split_workspace_bytes(S, n_per_stream, parts), dev)
+        with torch.cuda.device(dev), instrument.section("rng"):
+            _check(lib.gsb_legacy_normal_f32_split(_ptr(seeds_dev), S, n_per_stream, _ptr(out), n_per_stream, parts, _ptr(polys),
+                                                   _ptr(ws), ws.numel(), _stream()), "gsb_legacy_normal_f32_split")
+        instrument.count(3)
+        return out
     with torch.cuda.device(dev), instrument.section("rng"):
         _check(lib.gsb_legacy_normal_f32(_ptr(seeds_dev), S, n_per_stream, _ptr(out), n_per_stream, _stream()),
                "gsb_legacy_normal_f32")

@@ -22,6 +22,7 @@ is already being computed -- the result does not depend on the world size (SURVE
 from __future__ import annotations
 
 import datetime
+import inspect
 import os
 import sys
 from pathlib import Path
@@ -134,11 +135,9 @@ def _sample_batches_lazy(model, Bsz, seeds):
     """Like _sample_batches, plus ``ensure(row_end)``: rows [0, row_end) are final once it returns.  Models whose
     sample_latent has a second stage (StyleGAN2 W space: the mapping network) run it chunk by chunk on demand,
     so the IPCA chain starts on the first groups while later rows are still being mapped."""
-    if hasattr(model, "sample_latents_multi"):
-        try:
-            return model.sample_latents_multi(Bsz, seeds, lazy=True)
-        except TypeError:
-            pass
+    fn = getattr(model, "sample_latents_multi", None)
+    if fn is not None and "lazy" in inspect.signature(fn).parameters:
+        return fn(Bsz, seeds, lazy=True)
     return _sample_batches(model, Bsz, seeds), (lambda row_end: None)
 
 

@@ -181,30 +181,53 @@ class StyleGAN2(BaseModel):
         ``lazy=True`` (W space): returns (z, ensure) where ``ensure(row_end)`` maps rows [0, row_end) to W in
         place, chunk by chunk, so that the consumer of the first rows does not wait for the last ones."""
         S = len(seeds)
-        z = _native.legacy_normal(list(seeds), 512 * n_samples, self.device,
-                                  out=None if out is None else out.view(S, 512 * n_samples))
-        z = z.view(S * n_samples, 512)
-        if not self.w_primary:
-            return (z, lambda row_end: None) if lazy else z
-        if lazy:
-            packed = self.model.style.packed()
-            state = {"hi": 0}
-            total = z.shape[0]
+        parts = _native.split_parts(512 * n_samples)
+        if not lazy:
+            z = _native.legacy_normal(list(seeds), 512 * n_samples, self.device,
+                                      out=None if out is None else out.view(S, 512 * n_samples), parts=parts)
+            z = z.view(S * n_samples, 512)
+            if not self.w_primary:
+                return z
+            return self.model.style(z) if out is None else self.model.style.packed().forward(z, out=z)
+        # lazy: the streams are generated in launch groups on a side stream (a small first group, so that the first
+        # partial_fit group exists after ~1.5 ms instead of after the whole run's RNG); ensure(row_end) waits for the groups
+        # that cover rows [0, row_end) and, in W mode, maps them group by group in place.
+        z = torch.empty((S * n_samples, 512), dtype=torch.float32, device=self.device) if out is None else out.view(S * n_samples, 512)
+        sizes = [int(v) for v in os.environ.get("GANSPACE_B200_RNG_GROUPS", "4,10,18").split(",")]
+        bounds, g0 = [], 0
+        while g0 < S:
+            g1 = min(S, g0 + sizes[min(len(bounds), len(sizes) - 1)])
+            bounds.append((g0, g1))
+            g0 = g1
+        side = getattr(self, "_rng_stream", None)
+        if side is None:
+            with torch.cuda.device(self.device):
+                side = self._rng_stream = torch.cuda.Stream(device=self.device)
+        events = []
+        with torch.cuda.device(self.device):
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for (a, b) in bounds:
+                    _native.legacy_normal(list(seeds[a:b]), 512 * n_samples, self.device,
+                                          out=z[a * n_samples:b * n_samples].view(b - a, 512 * n_samples), parts=parts)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    events.append(ev)
+            z.record_stream(side)
+        packed = self.model.style.packed() if self.w_primary else None
+        state = {"g": 0}
+        free_sms = int(os.environ.get("GANSPACE_B200_LAZY_FREE_SMS", 48))   # tools/sweep_lazy.sh
 
-            first_rows = int(os.environ.get("GANSPACE_B200_LAZY_FIRST", max(4 * n_samples, 40_000)))
-            later_rows = int(os.environ.get("GANSPACE_B200_LAZY_LATER", max(10 * n_samples, 100_000)))
-            free_sms = int(os.environ.get("GANSPACE_B200_LAZY_FREE_SMS", 48))   # tools/sweep_lazy.sh
-
-            def ensure(row_end, first=first_rows, later=later_rows):
-                # a small first chunk lets the IPCA chain start early; later chunks are large (tile-quantisation
-                # and launch overheads) and leave a GPC's worth of SMs to the chain they run next to
-                while state["hi"] < min(row_end, total):
-                    a = state["hi"]
-                    b = min(total, a + (first if a == 0 else later))
-                    packed.forward(z[a:b], out=z[a:b], leave_free_sms=0 if a == 0 else free_sms)
-                    state["hi"] = b
-            return z, ensure
-        return self.model.style(z) if out is None else self.model.style.packed().forward(z, out=z)
+        def ensure(row_end):
+            # later groups run next to the IPCA chain and leave a GPC's worth of SMs to it
+            while state["g"] < len(bounds) and bounds[state["g"]][0] * n_samples < row_end:
+                g = state["g"]
+                a, b = bounds[g][0] * n_samples, bounds[g][1] * n_samples
+                torch.cuda.current_stream().wait_event(events[g])
+                if packed is not None:
+                    packed.forward(z[a:b], out=z[a:b], leave_free_sms=0 if g == 0 else free_sms)
+                state["g"] = g + 1
+        return z, ensure
 
     def check_numerics(self):
         """Raise if a kernel flagged an out-of-range activation since the weights were packed (synchronises)."""

@@ -39,7 +39,7 @@ def test_ctypes_signatures_match_header_prototypes():
             return None
         if "*" in decl or "gsb_stream_t" in decl:
             return C.c_void_p
-        for key, ct in (("int64_t", C.c_int64), ("size_t", C.c_size_t), ("double", C.c_double), ("float", C.c_float),
+        for key, ct in (("int64_t", C.c_int64), ("uint32_t", C.c_uint32), ("size_t", C.c_size_t), ("double", C.c_double), ("float", C.c_float),
                         ("unsigned", C.c_uint), ("int", C.c_int)):
             if re.search(rf"\b{key}\b", decl):
                 return ct
@@ -216,3 +216,22 @@ def test_generator_module_tree_and_init_order(golden):
     if "synth_param_sums" in gold:
         keys = [str(k) for k in gold["synth_param_keys"]]
         assert np.allclose([float(sd[k].double().sum()) for k in keys], gold["synth_param_sums"])
+
+
+def test_mt19937_jump_polynomials_match_numpy_state():
+    """Host side of the split RNG (csrc/rng_jump.cu): characteristic polynomial by Berlekamp-Massey, x^J mod phi, and the
+    jumped state as the XOR of state windows -- against NumPy's generator advanced J words (no GPU needed)."""
+    import ctypes as C
+    from ganspace_b200 import _native as nat
+    lib = nat.load()
+    step = int(lib.gsb_legacy_normal_split_step_words(512 * 1000, 4))
+    assert step > 0 and step % 624 == 0
+    polys = np.zeros((3, 624), np.uint32)
+    assert lib.gsb_mt19937_jump_polys(step, 3, polys.ctypes.data_as(C.c_void_p)) == 0
+    for seed, j in ((1791095845, 1), (5, 3)):
+        st = np.zeros(624, np.uint32)
+        assert lib.gsb_mt19937_jump_state_host(seed, polys[j - 1].ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p)) == 0
+        rs = np.random.RandomState(seed)
+        rs.randint(0, 2 ** 32, size=step * j, dtype=np.uint32)          # one word per draw
+        _, key, pos = rs.get_state()[:3]
+        assert pos == 624 and np.array_equal(key[1:], st[1:]) and (key[0] >> 31) == (st[0] >> 31)

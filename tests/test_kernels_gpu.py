@@ -130,6 +130,25 @@ def test_batch_stats_vs_oracle(nat, oracle, n, d):
     assert np.max(np.abs(g - g_ref)) < 3e-6 * np.max(np.abs(g_ref))
 
 
+@pytest.mark.parametrize("n,parts", [(20_000, 4), (512 * 1000, 2), (512 * 4000, 3), (512 * 10_000, 8)])
+def test_legacy_normal_split_streams_bit_exact(nat, oracle, n, parts):
+    """A stream generated by several CTAs (MT19937 jump-ahead + order-preserving compaction across sub-streams) is
+    bit-identical to the one-CTA stream, which is bit-identical to NumPy's RandomState.standard_normal."""
+    seeds = [1791095845, 7, 2147483646]
+    one = nat.legacy_normal(seeds, n, "cuda", parts=1)
+    many = nat.legacy_normal(seeds, n, "cuda", parts=parts)
+    torch.cuda.synchronize()
+    assert torch.equal(one, many)
+    if n <= 512 * 1000:
+        for i, s in enumerate(seeds):
+            assert np.array_equal(many[i].cpu().numpy(), oracle.standard_normal_f32(s, n))
+    flags = nat.C.c_uint(0)
+    lib = nat.load()
+    ws = nat.scratch.get("rng_split", 0, torch.device("cuda", torch.cuda.current_device()))
+    nat._check(lib.gsb_legacy_normal_split_status(nat._ptr(ws), len(seeds), n, parts, nat.C.byref(flags), nat._stream()), "status")
+    assert flags.value == 0
+
+
 @pytest.mark.parametrize("groups,nb,d", [(3, 2000, 512), (5, 777, 256), (2, 10000, 512), (4, 300, 96), (2, 64, 1024)])
 def test_batch_stats_multi_vs_fp64(nat, groups, nb, d):
     """Several partial_fit groups in one call (tensor-core Gram for d % 128 == 0, fp32 FMA kernels otherwise): every group's
