@@ -255,7 +255,10 @@ def legacy_normal(seeds, n_per_stream: int, device, out=None, parts: int = 1) ->
     ``parts`` > 1: every stream is generated by that many CTAs (MT19937 jump-ahead), bit-identical output."""
     lib = load()
     dev = require_cuda(device)
-    seeds_dev = _seeds_tensor(seeds, dev)
+    # ``seeds``: a list of ints, or an int32 device tensor from seeds_tensor() (no host->device copy on this call: a copy
+    # issued behind a long kernel would block the host until that kernel has finished)
+    seeds_dev = seeds if isinstance(seeds, torch.Tensor) else _seeds_tensor(seeds, dev)
+    assert seeds_dev.is_cuda and seeds_dev.dtype == torch.int32 and seeds_dev.is_contiguous()
     S = seeds_dev.numel()
     if out is None:
         out = torch.empty((S, n_per_stream), dtype=torch.float32, device=dev)
@@ -273,6 +276,22 @@ def legacy_normal(seeds, n_per_stream: int, device, out=None, parts: int = 1) ->
                "gsb_legacy_normal_f32")
     instrument.count(1)
     return out
+
+
+def seeds_tensor(seeds, dev):
+    return _seeds_tensor(seeds, dev)
+
+
+def rng_split_status(n_streams: int, n_per_stream: int, parts: int, device) -> int:
+    """Status word of the last split launch of this shape on ``device`` (0 = fine; synchronises)."""
+    lib = load()
+    dev = require_cuda(device)
+    ws = scratch.get("rng_split", lib.gsb_legacy_normal_split_workspace_bytes(n_streams, n_per_stream, parts), dev)
+    flags = C.c_uint(0)
+    with torch.cuda.device(dev):
+        _check(lib.gsb_legacy_normal_split_status(_ptr(ws), n_streams, n_per_stream, parts, C.byref(flags), _stream()),
+               "gsb_legacy_normal_split_status")
+    return int(flags.value)
 
 
 def _seeds_tensor(seeds, dev):

@@ -204,11 +204,18 @@ class StyleGAN2(BaseModel):
             with torch.cuda.device(self.device):
                 side = self._rng_stream = torch.cuda.Stream(device=self.device)
         events = []
+        seeds_dev = _native.seeds_tensor(list(seeds), self.device)       # ONE host->device copy, before any long kernel is queued
+        if parts > 1:
+            _native.jump_polys(512 * n_samples, parts, self.device)     # (first use: host computation + upload)
+            # one scratch buffer for the largest group, so that no launch re-allocates it while an earlier one is running
+            gmax = max(b - a for a, b in bounds)
+            _native.scratch.get("rng_split", _native.load().gsb_legacy_normal_split_workspace_bytes(gmax, 512 * n_samples, parts),
+                                _native.require_cuda(self.device)).record_stream(side)
         with torch.cuda.device(self.device):
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for (a, b) in bounds:
-                    _native.legacy_normal(list(seeds[a:b]), 512 * n_samples, self.device,
+                    _native.legacy_normal(seeds_dev[a:b], 512 * n_samples, self.device,
                                           out=z[a * n_samples:b * n_samples].view(b - a, 512 * n_samples), parts=parts)
                     ev = torch.cuda.Event()
                     ev.record(side)

@@ -142,11 +142,7 @@ def test_legacy_normal_split_streams_bit_exact(nat, oracle, n, parts):
     if n <= 512 * 1000:
         for i, s in enumerate(seeds):
             assert np.array_equal(many[i].cpu().numpy(), oracle.standard_normal_f32(s, n))
-    flags = nat.C.c_uint(0)
-    lib = nat.load()
-    ws = nat.scratch.get("rng_split", 0, torch.device("cuda", torch.cuda.current_device()))
-    nat._check(lib.gsb_legacy_normal_split_status(nat._ptr(ws), len(seeds), n, parts, nat.C.byref(flags), nat._stream()), "status")
-    assert flags.value == 0
+    assert nat.rng_split_status(len(seeds), n, parts, "cuda") == 0
 
 
 @pytest.mark.parametrize("groups,nb,d", [(3, 2000, 512), (5, 777, 256), (2, 10000, 512), (4, 300, 96), (2, 64, 1024)])
