@@ -144,11 +144,24 @@ class _Instrument:
         self.timing = False
         self._events = {}
         self.rows = {}
+        self.timeline = [] if os.environ.get("GANSPACE_B200_TIMELINE") == "1" else None
 
     def reset(self):
         self.launches = 0
         self._events = {}
         self.rows = {}
+
+    def mark(self, name):
+        """GANSPACE_B200_TIMELINE=1: a timed event on the current stream (tools/phase_probe.py prints them)."""
+        if self.timeline is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream())
+            self.timeline.append((name, ev))
+
+    def timeline_ms(self):
+        torch.cuda.synchronize()
+        t0 = self.timeline[0][1]
+        return [(n, t0.elapsed_time(e)) for n, e in self.timeline]
 
     def add_rows(self, name, n):
         """rows (samples) a section's kernels processed -- the roofline's unit count (bench.py)."""
@@ -171,6 +184,7 @@ class _Instrument:
             if self.o.timing:
                 self.e1.record(torch.cuda.current_stream())
                 self.o._events.setdefault(self.name, []).append((self.e0, self.e1))
+            self.o.mark(self.name + " done")
 
     def section(self, name):
         return self._Sec(self, name)
@@ -250,7 +264,7 @@ def split_parts(n_per_stream: int) -> int:
     return max(1, min(8, n_per_stream // 600_000))
 
 
-def legacy_normal(seeds, n_per_stream: int, device, out=None, parts: int = 1) -> torch.Tensor:
+def legacy_normal(seeds, n_per_stream: int, device, out=None, parts: int = 1, scratch_key: str = "rng_split") -> torch.Tensor:
     """RandomState(seed).standard_normal(n_per_stream).astype(float32) for every seed -> [S, n].
     ``parts`` > 1: every stream is generated by that many CTAs (MT19937 jump-ahead), bit-identical output."""
     lib = load()
@@ -265,11 +279,11 @@ def legacy_normal(seeds, n_per_stream: int, device, out=None, parts: int = 1) ->
     assert out.is_cuda and out.is_contiguous() and out.numel() >= S * n_per_stream
     if parts > 1 and S > 0 and n_per_stream >= 2 and n_per_stream % 2 == 0:
         polys = jump_polys(n_per_stream, parts, dev)
-        ws = scratch.get("rng_split", lib.gsb_legacy_normal_split_workspace_bytes(S, n_per_stream, parts), dev)
+        ws = scratch.get(scratch_key, lib.gsb_legacy_normal_split_workspace_bytes(S, n_per_stream, parts), dev)
         with torch.cuda.device(dev), instrument.section("rng"):
             _check(lib.gsb_legacy_normal_f32_split(_ptr(seeds_dev), S, n_per_stream, _ptr(out), n_per_stream, parts, _ptr(polys),
                                                    _ptr(ws), ws.numel(), _stream()), "gsb_legacy_normal_f32_split")
-        instrument.count(3)
+        instrument.count(2)
         return out
     with torch.cuda.device(dev), instrument.section("rng"):
         _check(lib.gsb_legacy_normal_f32(_ptr(seeds_dev), S, n_per_stream, _ptr(out), n_per_stream, _stream()),

@@ -199,28 +199,33 @@ class StyleGAN2(BaseModel):
             g1 = min(S, g0 + sizes[min(len(bounds), len(sizes) - 1)])
             bounds.append((g0, g1))
             g0 = g1
-        side = getattr(self, "_rng_stream", None)
-        if side is None:
+        sides = getattr(self, "_rng_streams", None)
+        if sides is None:                       # two streams, alternating groups: a group's start-up overlaps its predecessor's tail
             with torch.cuda.device(self.device):
-                side = self._rng_stream = torch.cuda.Stream(device=self.device)
+                sides = self._rng_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
         events = []
         seeds_dev = _native.seeds_tensor(list(seeds), self.device)       # ONE host->device copy, before any long kernel is queued
         if parts > 1:
             _native.jump_polys(512 * n_samples, parts, self.device)     # (first use: host computation + upload)
             # one scratch buffer for the largest group, so that no launch re-allocates it while an earlier one is running
             gmax = max(b - a for a, b in bounds)
-            _native.scratch.get("rng_split", _native.load().gsb_legacy_normal_split_workspace_bytes(gmax, 512 * n_samples, parts),
-                                _native.require_cuda(self.device)).record_stream(side)
+            for i, side in enumerate(sides):
+                _native.scratch.get(f"rng_split{i}", _native.load().gsb_legacy_normal_split_workspace_bytes(gmax, 512 * n_samples, parts),
+                                    _native.require_cuda(self.device)).record_stream(side)
         with torch.cuda.device(self.device):
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for (a, b) in bounds:
+            for side in sides:
+                side.wait_stream(torch.cuda.current_stream())
+            for gi, (a, b) in enumerate(bounds):
+                side = sides[gi % len(sides)]
+                with torch.cuda.stream(side):
                     _native.legacy_normal(seeds_dev[a:b], 512 * n_samples, self.device,
-                                          out=z[a * n_samples:b * n_samples].view(b - a, 512 * n_samples), parts=parts)
+                                          out=z[a * n_samples:b * n_samples].view(b - a, 512 * n_samples), parts=parts,
+                                          scratch_key=f"rng_split{gi % len(sides)}")
                     ev = torch.cuda.Event()
                     ev.record(side)
                     events.append(ev)
-            z.record_stream(side)
+            for side in sides:
+                z.record_stream(side)
         packed = self.model.style.packed() if self.w_primary else None
         state = {"g": 0}
         free_sms = int(os.environ.get("GANSPACE_B200_LAZY_FREE_SMS", 48))   # tools/sweep_lazy.sh
