@@ -1466,6 +1466,46 @@ extern "C" int gsb_ipca_chain_step(void *d_state, int d, int c, int64_t n_seen, 
     return GSB_OK;
 }
 
+// ---- persistent chain (subspace.cu): steps k_begin .. k_end-1 in ONE launch, fed through a queue -----------------------------
+extern "C" int gsb_ipca_chain_persistent_supported(int d, int c) { return gsb::subspace_applicable(d, c) ? 1 : 0; }
+
+extern "C" size_t gsb_ipca_queue_bytes(int n_groups) { return gsb::chain_queue_bytes(n_groups); }
+
+extern "C" int gsb_ipca_queue_reset(void *d_queue, int n_groups, gsb_stream_t stream) {
+    GSB_CHECK_ARG(d_queue && n_groups > 0, "ipca_queue_reset: bad arguments");
+    return gsb::chain_queue_reset(d_queue, n_groups, (cudaStream_t)stream);
+}
+
+extern "C" int gsb_ipca_queue_publish(void *d_queue, int n_groups, int k0, int count, const double *d_mean_base,
+                                      const double *d_gram_base, int d, int round_first, int world, int per_rank, int flag,
+                                      gsb_stream_t stream) {
+    GSB_CHECK_ARG(d_queue && k0 >= 0 && count >= 1 && k0 + count <= n_groups && (flag == 1 || flag == 2) && world >= 1 && per_rank >= 1,
+                  "ipca_queue_publish: bad arguments (k0=%d count=%d groups=%d flag=%d)", k0, count, n_groups, flag);
+    GSB_CHECK_ARG(flag == 2 || (d_mean_base && d_gram_base), "ipca_queue_publish: null statistics");
+    return gsb::chain_queue_publish(d_queue, k0, count, d_mean_base, d_gram_base, d, round_first, world, per_rank, flag,
+                                    (cudaStream_t)stream);
+}
+
+extern "C" int gsb_ipca_chain_run(void *d_state, int d, int c, int64_t n_batch, void *d_queue, int n_groups, int k_begin, int k_end,
+                                  void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
+    GSB_CHECK_ARG(d_state && d_queue && d_workspace, "ipca_chain_run: null pointer");
+    if (int r = gsb::check_dims(d, c)) return r;
+    GSB_CHECK_ARG(gsb::subspace_applicable(d, c), "ipca_chain_run: shape (d=%d, c=%d) has no persistent chain kernel", d, c);
+    GSB_CHECK_ARG(n_batch > 0 && k_begin >= 1 && k_begin <= k_end && k_end <= n_groups, "ipca_chain_run: bad step range [%d, %d) of %d",
+                  k_begin, k_end, n_groups);
+    gsb::Workspace w = gsb::carve(d_workspace, d, c);
+    size_t off = w.bytes;
+    if (gsb::lanczos_applicable(d, c)) off += gsb::carve_lanczos(nullptr, d, c).bytes;
+    gsb::SubspaceWs sw = gsb::carve_subspace(reinterpret_cast<char *>(d_workspace) + off, d, c);
+    if (workspace_bytes < off + sw.bytes) {
+        gsb::set_error("ipca_chain_run: workspace too small (%zu < %zu)", workspace_bytes, off + sw.bytes);
+        return GSB_ERR_WORKSPACE;
+    }
+    gsb::StateView s = gsb::state_view(d_state, d, c);
+    return gsb::subspace_run_persistent(s.hdr, s.mean, s.unnorm, s.H, s.Qbuf, sw, d, c, (double)n_batch, d_queue, n_groups, k_begin,
+                                        k_end, (cudaStream_t)stream);
+}
+
 extern "C" int gsb_ipca_export(const void *d_state, int d, int c, int64_t n_seen, double *d_components,
                                double *d_singular_values, double *d_mean, double *d_var,
                                double *d_explained_variance, double *d_explained_variance_ratio,

@@ -30,6 +30,13 @@ size_t subspace_smem_bytes(int d, int c);
 SubspaceWs carve_subspace(void *base, int d, int c);
 int subspace_step(double *hdr, double *mean, double *unnorm, double *H, double *Qbuf, const double *mean_b, const double *gram_b,
                   const SubspaceWs &w, int d, int c, double n_seen, double n_b, cudaStream_t st);
+// persistent form: the cluster stays resident for steps k_begin .. k_end-1 and takes (mean, Gram) pointers from a queue
+size_t chain_queue_bytes(int n_groups);
+int chain_queue_reset(void *queue, int n_groups, cudaStream_t st);
+int chain_queue_publish(void *queue, int k0, int count, const double *mean_base, const double *gram_base, int d, int round_first,
+                        int world, int per_rank, int flag, cudaStream_t st);
+int subspace_run_persistent(double *hdr, double *mean, double *unnorm, double *H, double *Qbuf, const SubspaceWs &w, int d, int c,
+                            double n_b, void *queue, int n_groups, int k_begin, int k_end, cudaStream_t st);
 int to_subspace_form(double *hdr, const double *S, const double *V, double *H, double *Qbuf, int d, int c, cudaStream_t st);
 int materialise_components(double *hdr, double *S, double *V, const double *H, const double *Qbuf, void *eig_ws, int d, int c,
                            cudaStream_t st);

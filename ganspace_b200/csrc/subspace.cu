@@ -42,7 +42,7 @@ struct SubspaceParams {
     double *Gt, *Part, *Red, *Slots;             // workspace: G tiles, per-CTA partial (H~, W), reduced (H~, W), scalars
     double *Prof;                                // [16] clocks per phase, accumulated by CTA 0 (profiling aid)
     int d, c;
-    double n_seen, n_b, tol;
+    double n_seen, n_b, tol;                     // n_seen < 0: read it from hdr[0] (persistent kernel)
     int maxit;
     int *status;
 };
@@ -190,9 +190,11 @@ __device__ __forceinline__ void chol_solve_regs(const double *__restrict__ Ws, d
     __syncthreads();
 }
 
+// One chain step by the whole cluster (every thread of every CTA calls it with the same p).  All data written by one CTA and
+// read by another travels through L2 (.cg loads / cp.async.cg) or after a cluster barrier, so the function can be called
+// repeatedly from a persistent kernel.
 template <int RA, int CB>
-__global__ void __launch_bounds__(SC_THREADS, 1)
-subspace_step_kernel(const SubspaceParams p) {
+__device__ __forceinline__ void subspace_step_body(const SubspaceParams &p) {
     extern __shared__ __align__(16) double sc_smem[];
     const int d = p.d, c = p.c, cp = c + 4, RPC = d / SC_CL, RT = RPC / 8, CT = c / 8, nkt = d / SC_KT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fg = lane >> 2, ft = lane & 3;
@@ -212,8 +214,8 @@ subspace_step_kernel(const SubspaceParams p) {
     double prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define PROF(k) do { const long long tn_ = clock64(); prof[k] += (double)(tn_ - tprev); tprev = tn_; } while (0)
 
-    const double n_seen = p.n_seen, n_b = p.n_b, n_tot = n_seen + n_b;
-    int cur = (int)p.hdr[3];
+    const double n_seen = (p.n_seen >= 0.0) ? p.n_seen : __ldcg(p.hdr), n_b = p.n_b, n_tot = n_seen + n_b;   // persistent: from the state
+    int cur = (int)__ldcg(p.hdr + 3);
     double *Qc = p.Qbuf + (size_t)cur * d * cp, *Qn = p.Qbuf + (size_t)(cur ^ 1) * d * cp;
     const size_t tileA = (size_t)RPC * SC_LDA, tileB = (size_t)SC_KT * cp;
     double *Gmine = p.Gt + (size_t)me * nkt * tileA;
@@ -221,7 +223,7 @@ subspace_step_kernel(const SubspaceParams p) {
     // ------------------------------------------------------------------ phase 0: m, own rows of Q, H
     {
         const double f = sqrt((n_seen / n_tot) * n_b);
-        for (int i = tid; i < d; i += SC_THREADS) mv[i] = f * (p.mean[i] - p.mean_b[i]);
+        for (int i = tid; i < d; i += SC_THREADS) mv[i] = f * (__ldcg(p.mean + i) - __ldcg(p.mean_b + i));
         const double *src = Qc + (size_t)me * RPC * cp;
         for (int i = tid; i < RPC * cp; i += SC_THREADS) Qq[i] = __ldcg(src + i);
         for (int i = tid; i < c * c; i += SC_THREADS) Ws[(i / c) * cp + i % c] = __ldcg(p.H + i);
@@ -470,11 +472,11 @@ subspace_step_kernel(const SubspaceParams p) {
     }
     for (int l = tid; l < RPC; l += SC_THREADS) {
         const int i = me * RPC + l;
-        const double mb = p.mean_b[i], vb = p.gram_b[(size_t)i * d + i], mo = p.mean[i];
+        const double mb = __ldcg(p.mean_b + i), vb = __ldcg(p.gram_b + (size_t)i * d + i), mo = __ldcg(p.mean + i);
         // extmath._incremental_mean_and_var (same arithmetic as finalize_kernel in ipca.cu)
         const double r = n_seen / n_b;
         const double tq = (mo * n_seen) / r - mb * n_b;
-        p.unnorm[i] = p.unnorm[i] + vb + r / n_tot * tq * tq;
+        p.unnorm[i] = __ldcg(p.unnorm + i) + vb + r / n_tot * tq * tq;
         p.mean[i] = (mo * n_seen + mb * n_b) / n_tot;
     }
     __syncthreads();
@@ -493,7 +495,76 @@ subspace_step_kernel(const SubspaceParams p) {
         p.Prof[9] += (double)it;
         p.Prof[10] += 1.0;
     }
+    __syncthreads();
     sc_cluster_sync();
+}
+#undef PROF
+
+template <int RA, int CB>
+__global__ void __launch_bounds__(SC_THREADS, 1)
+subspace_step_kernel(const SubspaceParams p) {
+    subspace_step_body<RA, CB>(p);
+}
+
+// ---- persistent form: the cluster stays resident and takes the groups' statistics from a queue ---------------------------------
+// A step per launch needs 16 free SMs of one GPC at every launch; next to the producers' long-running CTAs (RNG sub-streams,
+// persistent GEMM CTAs) each launch waited up to a millisecond.  The persistent kernel occupies its 16 SMs once, for steps
+// k_begin .. k_end-1, and waits for entry k of the queue (pointers to the group's mean / centred Gram, then a flag) which a
+// one-warp kernel on the producers' stream publishes behind the statistics kernels.
+struct ChainQueueEntry {
+    const double *mean, *gram;
+    int flag;                // 0 = not published, 1 = ready, 2 = stop before this step
+    int pad;
+};
+
+__global__ void chain_publish_kernel(ChainQueueEntry *q, int k0, int count, const double *mean_base, const double *gram_base, int d,
+                                     int round_first, int world, int per_rank, int flag) {
+    const int i = threadIdx.x + blockIdx.x * blockDim.x;
+    if (i >= count) return;
+    const int k = k0 + i;
+    // slot of group k inside the buffers: linear (world = 1), or the all-gather layout of a round (plan.rounds):
+    // rank (k mod world) contributed its (k - round_first) / world -th group
+    const size_t slot = (world <= 1) ? (size_t)i : (size_t)(k % world) * per_rank + (size_t)(k - round_first) / world;
+    q[k].mean = mean_base ? mean_base + slot * d : nullptr;
+    q[k].gram = gram_base ? gram_base + slot * (size_t)d * d : nullptr;
+    __threadfence();
+    *reinterpret_cast<volatile int *>(&q[k].flag) = flag;
+}
+
+template <int RA, int CB>
+__global__ void __launch_bounds__(SC_THREADS, 1)
+subspace_persistent_kernel(SubspaceParams p, ChainQueueEntry *queue, int *decision, int k_begin, int k_end, double timeout_ns) {
+    __shared__ int s_dec;
+    uint32_t me;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(me));
+    for (int k = k_begin; k < k_end; ++k) {
+        if (me == 0 && threadIdx.x == 0) {
+            // CTA 0 alone polls (the others sleep in the cluster barrier) and decides for the whole cluster
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            int f;
+            unsigned ns = 64;
+            for (;;) {
+                f = *reinterpret_cast<volatile int *>(&queue[k].flag);
+                if (f != 0) break;
+                __nanosleep(ns);
+                if (ns < 2048) ns *= 2;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if ((double)(t1 - t0) > timeout_ns) { f = 3; break; }          // producer never came: give up, flag the run
+            }
+            __threadfence();
+            *reinterpret_cast<volatile int *>(decision) = f;
+            if (f == 3) atomicOr(p.status, 8);
+        }
+        __syncthreads();
+        sc_cluster_sync();
+        if (threadIdx.x == 0) s_dec = *reinterpret_cast<volatile int *>(decision);
+        __syncthreads();
+        if (s_dec != 1) break;
+        p.mean_b = *reinterpret_cast<const double *volatile *>(&queue[k].mean);
+        p.gram_b = *reinterpret_cast<const double *volatile *>(&queue[k].gram);
+        subspace_step_body<RA, CB>(p);
+    }
 }
 
 // (V, S) of the direct first step -> (Q, H):  Q[i][t] = V[t][i], H = diag(S^2)
@@ -628,6 +699,67 @@ int subspace_step(double *hdr, double *mean, double *unnorm, double *H, double *
     at[0].val.clusterDim.x = SC_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     GSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    return GSB_OK;
+}
+
+// ---- persistent chain: host side -------------------------------------------------------------------------------------------
+size_t chain_queue_bytes(int n_groups) { return align_up((size_t)n_groups * sizeof(ChainQueueEntry), 256) + 256; }
+
+int chain_queue_reset(void *queue, int n_groups, cudaStream_t st) {
+    GSB_CHECK_CUDA(cudaMemsetAsync(queue, 0, chain_queue_bytes(n_groups), st));
+    return GSB_OK;
+}
+
+int chain_queue_publish(void *queue, int k0, int count, const double *mean_base, const double *gram_base, int d, int round_first,
+                        int world, int per_rank, int flag, cudaStream_t st) {
+    chain_publish_kernel<<<(count + 31) / 32, 32, 0, st>>>(reinterpret_cast<ChainQueueEntry *>(queue), k0, count, mean_base, gram_base,
+                                                         d, round_first, world, per_rank, flag);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
+int subspace_run_persistent(double *hdr, double *mean, double *unnorm, double *H, double *Qbuf, const SubspaceWs &w, int d, int c,
+                            double n_b, void *queue, int n_groups, int k_begin, int k_end, cudaStream_t st) {
+    double tol;
+    int maxit;
+    {
+        const char *e1 = getenv("GANSPACE_B200_SUBSPACE_TOL"), *e2 = getenv("GANSPACE_B200_SUBSPACE_MAXIT");
+        tol = e1 ? atof(e1) : 1e-4;
+        if (!(tol > 0.0)) tol = 1e-4;
+        maxit = e2 ? atoi(e2) : 60;
+        if (maxit < 1) maxit = 60;
+    }
+    const char *et = getenv("GANSPACE_B200_CHAIN_TIMEOUT_S");
+    const double timeout_ns = 1e9 * (et ? atof(et) : 10.0);
+    const size_t smem = subspace_smem_bytes(d, c);
+    const bool small = (c <= 80 && c + d / SC_CL <= 112);
+    auto kern = small ? subspace_persistent_kernel<7, 5> : subspace_persistent_kernel<10, 8>;
+    static size_t smem_set[2] = {0, 0};
+    static bool cluster_set[2] = {false, false};
+    if (!cluster_set[small]) {
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cluster_set[small] = true;
+    }
+    if (smem > smem_set[small]) {
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[small] = smem;
+    }
+    SubspaceParams p;
+    p.hdr = hdr; p.mean = mean; p.unnorm = unnorm; p.H = H; p.Qbuf = Qbuf;
+    p.mean_b = nullptr; p.gram_b = nullptr;
+    p.Gt = w.Gt; p.Part = w.Part; p.Red = w.Red; p.Slots = w.Slots; p.Prof = hdr + 8;
+    p.d = d; p.c = c; p.n_seen = -1.0; p.n_b = n_b; p.tol = tol; p.maxit = maxit;
+    p.status = eig_status_device_ptr();
+    GSB_CHECK_ARG(p.status, "subspace_run_persistent: no device status word");
+    ChainQueueEntry *q = reinterpret_cast<ChainQueueEntry *>(queue);
+    int *decision = reinterpret_cast<int *>(reinterpret_cast<char *>(queue) + align_up((size_t)n_groups * sizeof(ChainQueueEntry), 256));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(SC_CL); cfg.blockDim = dim3(SC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = SC_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p, q, decision, k_begin, k_end, timeout_ns));
     return GSB_OK;
 }
 

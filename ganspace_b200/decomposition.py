@@ -334,6 +334,8 @@ def compute_arrays(config, instrumented_model, state=None):
     k = 0
     stop = False                 # fit_partial returned False (e.g. n_components > first batch): the reference leaves the loop (:262-263)
     exchange = _StatsExchange(d, world) if (live and not large_d) else None
+    if not large_d and hasattr(tr, "begin_run"):
+        tr.begin_run(K, NB, d, device)           # groups 1 .. K-1 merge inside one resident chain kernel (csrc/subspace.cu)
 
     def group_rows(rows):
         """[n, d] activations of the hooked layer for latent rows ``rows`` (small-d engine; n is a multiple of NB)."""
@@ -442,6 +444,9 @@ def compute_arrays(config, instrumented_model, state=None):
         # the reference's `gi` of the interrupted group (:268-272) = the samples merged so far
         state["canceled_at"] = int(tr.n_samples_seen_)
 
+    finally:
+        if hasattr(tr, "end_run"):
+            tr.end_run()                                # a resident chain kernel never waits for groups that will not come
     tick("sampling + activations + IPCA chain")
     X_comp, X_stdev, X_var_ratio = transformer.get_components()
     X_comp = np.array(X_comp, copy=True)
