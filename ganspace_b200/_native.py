@@ -515,7 +515,10 @@ class IPCAChain:
         """Declare a run of ``n_groups`` equal batches.  Returns False (and changes nothing) when the shape has no persistent
         kernel or GANSPACE_B200_CHAIN_PERSISTENT=0; then every step() is its own launch."""
         lib = load()
-        if (n_groups < 2 or self.n_seen != 0 or os.environ.get("GANSPACE_B200_CHAIN_PERSISTENT", "1") == "0"
+        # Opt-in (GANSPACE_B200_CHAIN_PERSISTENT=1).  Measured on config 2: no gain over one launch per step once the producers
+        # leave SMs free, and a hazard: with CUDA's lazy module loading the first launch of any not-yet-loaded kernel blocks until
+        # the resident kernel exits (it then gives up after its timeout).  Use with CUDA_MODULE_LOADING=EAGER or after a warm-up.
+        if (n_groups < 2 or self.n_seen != 0 or os.environ.get("GANSPACE_B200_CHAIN_PERSISTENT", "0") != "1"
                 or not lib.gsb_ipca_chain_persistent_supported(self.d, self.c)):
             return False
         self._run = {"K": int(n_groups), "nb": int(n_batch), "next": 0, "keep": [], "closed": False}

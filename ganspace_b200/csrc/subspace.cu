@@ -707,6 +707,9 @@ size_t chain_queue_bytes(int n_groups) { return align_up((size_t)n_groups * size
 
 int chain_queue_reset(void *queue, int n_groups, cudaStream_t st) {
     GSB_CHECK_CUDA(cudaMemsetAsync(queue, 0, chain_queue_bytes(n_groups), st));
+    // an empty publish: with lazy module loading the kernel's first launch would otherwise block until the resident kernel exits
+    chain_publish_kernel<<<1, 32, 0, st>>>(reinterpret_cast<ChainQueueEntry *>(queue), 0, 0, nullptr, nullptr, 0, 0, 1, 1, 0);
+    GSB_CHECK_LAUNCH();
     return GSB_OK;
 }
 

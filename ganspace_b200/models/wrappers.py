@@ -193,16 +193,20 @@ class StyleGAN2(BaseModel):
         # partial_fit group exists after ~1.5 ms instead of after the whole run's RNG); ensure(row_end) waits for the groups
         # that cover rows [0, row_end) and, in W mode, maps them group by group in place.
         z = torch.empty((S * n_samples, 512), dtype=torch.float32, device=self.device) if out is None else out.view(S * n_samples, 512)
-        sizes = [int(v) for v in os.environ.get("GANSPACE_B200_RNG_GROUPS", "4,10,18").split(",")]
+        # group sizes in streams (x parts CTAs each).  Measured (tools/phase_probe.py, config 2): the merge chain's 16-CTA cluster
+        # launches need free SMs at every step, so the producers share the machine statically -- 7 streams x 8 = 56 RNG CTAs,
+        # 76 persistent GEMM CTAs (GANSPACE_B200_LAZY_FREE_SMS = 72), 16 SMs for the chain
+        sizes = [int(v) for v in os.environ.get("GANSPACE_B200_RNG_GROUPS", "4,7").split(",")]
         bounds, g0 = [], 0
         while g0 < S:
             g1 = min(S, g0 + sizes[min(len(bounds), len(sizes) - 1)])
             bounds.append((g0, g1))
             g0 = g1
         sides = getattr(self, "_rng_streams", None)
-        if sides is None:                       # two streams, alternating groups: a group's start-up overlaps its predecessor's tail
+        if sides is None:                       # (more than one stream: groups alternate; measured slower -- they crowd out the GEMMs)
             with torch.cuda.device(self.device):
-                sides = self._rng_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+                sides = self._rng_streams = [torch.cuda.Stream(device=self.device)
+                                             for _ in range(max(1, int(os.environ.get("GANSPACE_B200_RNG_STREAMS", "1"))))]
         events = []
         seeds_dev = _native.seeds_tensor(list(seeds), self.device)       # ONE host->device copy, before any long kernel is queued
         if parts > 1:
@@ -228,7 +232,7 @@ class StyleGAN2(BaseModel):
                 z.record_stream(side)
         packed = self.model.style.packed() if self.w_primary else None
         state = {"g": 0}
-        free_sms = int(os.environ.get("GANSPACE_B200_LAZY_FREE_SMS", 48))   # tools/sweep_lazy.sh
+        free_sms = int(os.environ.get("GANSPACE_B200_LAZY_FREE_SMS", 72 if parts > 1 else 48))
 
         def ensure(row_end):
             # later groups run next to the IPCA chain and leave a GPC's worth of SMs to it

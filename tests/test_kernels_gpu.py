@@ -222,7 +222,7 @@ def test_ipca_chain_vs_oracle_gram_d512(nat, oracle, mapping_weights):
     assert np.max(np.abs(out["explained_variance_ratio"] - st.explained_variance_ratio)) < 1e-6
 
 
-def test_persistent_chain_equals_step_launches(nat, oracle, mapping_weights):
+def test_persistent_chain_equals_step_launches(nat, oracle, mapping_weights, monkeypatch):
     """The resident chain kernel (one launch for steps 1..K-1, statistics handed over through the device queue) performs the
     same arithmetic as one launch per step; an early end_run() stops it after the published groups."""
     ws, bs = mapping_weights
@@ -234,6 +234,7 @@ def test_persistent_chain_equals_step_launches(nat, oracle, mapping_weights):
     for m, G in stats:
         ref.step(2500, m, G)
     ref_out = {k: v.cpu().numpy() for k, v in ref.export().items()}
+    monkeypatch.setenv("GANSPACE_B200_CHAIN_PERSISTENT", "1")          # opt-in feature
     run = nat.IPCAChain(512, 80, "cuda")
     assert run.begin_run(6, 2500)
     for m, G in stats:
