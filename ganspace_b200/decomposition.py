@@ -212,10 +212,12 @@ def compute(config, dump_name, instrumented_model):
     rank, world, live = _dist()
     if rank == 0:
         os.makedirs(dump_name.parent, exist_ok=True)
-        # same 8-array .npz; conv feature maps (act_comp = 168 MB at convs.4) are stored uncompressed: single-core
-        # deflate of incompressible float32 data would cost more than the whole device computation
-        big = sum(a.nbytes for a in arrays.values()) > (64 << 20)
-        (np.savez if big else np.savez_compressed)(dump_name, **arrays)
+        # same 8-array .npz container, read by np.load exactly like the reference's; stored WITHOUT deflate: the arrays are
+        # float32 noise (7 % smaller compressed) and single-core zlib costs 8-18 ms for config 2 -- a fifth of the whole
+        # device run -- and minutes for conv feature maps (act_comp = 168 MB at convs.4).  GANSPACE_B200_NPZ_COMPRESS=1 restores
+        # np.savez_compressed (decomposition.py:331-341).
+        compress = os.environ.get("GANSPACE_B200_NPZ_COMPRESS") == "1" and sum(a.nbytes for a in arrays.values()) <= (64 << 20)
+        (np.savez_compressed if compress else np.savez)(dump_name, **arrays)
     if live:
         import torch.distributed as dist
         dist.barrier()
