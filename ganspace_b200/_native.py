@@ -35,6 +35,7 @@ SIGNATURES = {
     "gsb_mapping_forward": (_I, [_P, _I, _I, _P, _P, _L, _I, _P, _Z, _P]),
     "gsb_mapping_status": (_I, [_P, _I, _I, _P]),
     "gsb_linear_forward": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P, _Z, _P]),
+    "gsb_linear_workspace_bytes": (_Z, [_L, _I, _I, _I]),
     "gsb_batch_stats_workspace_bytes": (_Z, [_L, _I]),
     "gsb_batch_stats": (_I, [_P, _L, _I, _L, _P, _P, _P, _Z, _P]),
     "gsb_batch_stats_multi_workspace_bytes": (_Z, [_I, _L, _I]),
@@ -204,7 +205,7 @@ instrument = _Instrument()
 # the kernels behind each timed section (bench.py's roofline names the one it reports)
 SECTION_KERNELS = {
     "mapping": "mapping MLP: pixelnorm_split + 8 x mapping_layer_tc_kernel (tcgen05, fp16 hi/lo x3)",
-    "linear": "gen_z linear: sgemm_tn_bias_act_kernel",
+    "linear": "gen_z linear: mapping_layer_tc_kernel (tcgen05, fp16 hi/lo x3, bias epilogue, TMA store) for n >= 128",
     "synthesis": "StyledConv chain: tap-GEMM tc_gemm_plain (tcgen05) + gather/scatter/blur epilogues",
 }
 
@@ -395,8 +396,9 @@ class PackedMapping:
         return out.reshape(z.shape)
 
 
-def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor = None, lrelu: bool = False) -> torch.Tensor:
-    """y = x @ w.T (+ bias) in the fp32 FMA GEMM kernel; x [n,K], w [N,K] (N % 128 == 0, K % 16 == 0)."""
+def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor = None, lrelu: bool = False, bounded: bool = False) -> torch.Tensor:
+    """y = x @ w.T (+ bias); x [n,K], w [N,K] (N % 128 == 0, K % 16 == 0).  ``bounded`` (|x| < 6e4 guaranteed by the caller)
+    lets n >= 128, N % 256 == 0, K % 64 == 0 run on the tensor cores (fp32-grade); otherwise the fp32 FMA GEMM kernel."""
     lib = load()
     assert x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and x.shape[-1] == w.shape[1]
     x2 = x.reshape(-1, x.shape[-1]).contiguous()
@@ -404,11 +406,12 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor = None, lrelu: b
     n, K = x2.shape
     N = w.shape[0]
     y = torch.empty((n, N), dtype=torch.float32, device=x.device)
-    ws = scratch.get("linear", 4 * N, x.device)
+    flags = (1 if lrelu else 0) | (2 if bounded else 0)
+    ws = scratch.get("linear", lib.gsb_linear_workspace_bytes(n, N, K, flags), x.device)
     with torch.cuda.device(x.device), instrument.section("linear"):
         _check(lib.gsb_linear_forward(_ptr(x2), _ptr(w), _ptr(bias.contiguous() if bias is not None else None), _ptr(y),
-                                      n, N, K, 1 if lrelu else 0, _ptr(ws), ws.numel(), _stream()), "gsb_linear_forward")
-    instrument.count(1)
+                                      n, N, K, flags, _ptr(ws), ws.numel(), _stream()), "gsb_linear_forward")
+    instrument.count(5 if (bounded and n >= 128 and N % 256 == 0 and K % 64 == 0) else 1)
     instrument.add_rows("linear", n)
     return y.reshape(*x.shape[:-1], N)
 

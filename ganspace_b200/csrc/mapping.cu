@@ -20,6 +20,9 @@ int mapping_tc_pack(const float *pw, int n_layers, int dim, void *tc_base, cudaS
 int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim, const float *d_z, float *d_w,
                        int64_t n, bool pixelnorm, void *ws, int leave_free_sms, cudaStream_t st);
 size_t mapping_tc_workspace_bytes(int64_t n, int dim);
+size_t tc_linear_workspace_bytes(int64_t n, int N, int K);
+int tc_linear(const float *x, const float *w, const float *bias, float *y, int64_t n, int N, int K, bool lrelu, void *ws,
+              cudaStream_t st);
 unsigned *mapping_tc_overflow_flag(void *tc_base, int n_layers, int dim);
 
 static inline size_t simt_packed_bytes(int n_layers, int dim) {
@@ -247,6 +250,20 @@ extern "C" int gsb_mapping_status(const void *d_packed, int n_layers, int dim, u
 // Generic affine layer  y[n,N] = x[n,K] * W[N,K]^T + bias[N]  (bias may be NULL), optional sqrt2*lrelu.
 //   replaces  nn.Linear / F.linear call sites of the path outside the mapping network, e.g. BigGAN's
 //   generator.gen_z (biggan model.py:211-212,232; spectral norm folded into W by the caller).
+// bit 1 of flags (the caller vouches that |x| stays inside fp16's range) selects the tcgen05 kernel for shapes it covers
+static bool linear_tc_eligible(int64_t n, int N, int K, int flags) {
+    return (flags & 2) && n >= 128 && N % 256 == 0 && K % 64 == 0;
+}
+
+extern "C" size_t gsb_linear_workspace_bytes(int64_t n, int N, int K, int flags) {
+    size_t b = (size_t)N * sizeof(float);
+    if (linear_tc_eligible(n, N, K, flags)) {
+        size_t t = gsb::tc_linear_workspace_bytes(n, N, K) + gsb::align_up((size_t)N * sizeof(float), 256);
+        if (t > b) b = t;
+    }
+    return b;
+}
+
 extern "C" int gsb_linear_forward(const float *d_x, const float *d_w, const float *d_bias, float *d_y, int64_t n,
                                   int N, int K, int flags, void *d_workspace, size_t workspace_bytes,
                                   gsb_stream_t stream) {
@@ -254,6 +271,13 @@ extern "C" int gsb_linear_forward(const float *d_x, const float *d_w, const floa
     GSB_CHECK_ARG(n >= 0 && N > 0 && K > 0 && N % 128 == 0 && K % 16 == 0, "linear_forward: need N%%128==0, K%%16==0 (N=%d K=%d)", N, K);
     if (n == 0) return GSB_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (linear_tc_eligible(n, N, K, flags) && d_workspace && workspace_bytes >= gsb_linear_workspace_bytes(n, N, K, flags)) {
+        // tensor cores (tcgen05, fp16 hi/lo split operands = fp32-grade): zero bias first if none was given
+        float *zb = reinterpret_cast<float *>(d_workspace);
+        char *rest = reinterpret_cast<char *>(d_workspace) + gsb::align_up((size_t)N * sizeof(float), 256);
+        if (!d_bias) GSB_CHECK_CUDA(cudaMemsetAsync(zb, 0, (size_t)N * sizeof(float), st));
+        return gsb::tc_linear(d_x, d_w, d_bias ? d_bias : zb, d_y, n, N, K, (flags & 1) != 0, rest, st);
+    }
     const float *bias = d_bias;
     if (!bias) {
         if (!d_workspace || workspace_bytes < (size_t)N * sizeof(float)) {

@@ -163,7 +163,7 @@ struct TcParams {
     unsigned *overflow;     // set to 1 when an activation leaves fp16's range
     const float *inv_wscale;   // device pointer to 2^-s of this layer
     int M, N_total, K;
-    int mode;               // 0: (acc 2^-s + bias) -> leaky-ReLU * sqrt2 (EqualLinear);  1: plain acc 2^-s (tc_gemm_plain)
+    int mode;               // 0: (acc 2^-s + bias) -> leaky-ReLU * sqrt2 (EqualLinear);  1: plain acc 2^-s (tc_gemm_plain);  2: acc 2^-s + bias
     int n_groups;           // work units per cluster tile (1 or N_total / 256)
     int dbg;                // profiling experiments (GANSPACE_B200_MAPPING_DBG): 1 no stores, 2 no W loads, 4 no A loads, 8 no MMAs
 };
@@ -321,7 +321,7 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
                     mbar_arrive(&tempty_bar[acc]);
                 }
                 if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging has been read out
-                if (c0 == 0 && p.mode == 0) {                      // (safe: the previous tile's readers passed a barrier below)
+                if (c0 == 0 && p.mode != 1) {                      // (safe: the previous tile's readers passed a barrier below)
                     bias_s[et] = __ldg(&p.bias[n0 + et]);
                     bias_s[et + 128] = __ldg(&p.bias[n0 + et + 128]);
                 }
@@ -330,8 +330,8 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
 #pragma unroll
                 for (int j = 0; j < 64; ++j) {
                     float x = __fmul_rn(__uint_as_float(v[j]), inv_wscale);
+                    if (p.mode != 1) x += bias_s[c0 + j];
                     if (p.mode == 0) {
-                        x += bias_s[c0 + j];
                         x = (x >= 0.f) ? x : __fmul_rn(x, 0.2f);
                         x = __fmul_rn(sqrt2, x);
                     }
@@ -647,6 +647,43 @@ int tc_gemm_plain(const __half *a_hi, const __half *a_lo, int64_t M, int K, cons
     p.bias = nullptr; p.out_hi = nullptr; p.out_lo = nullptr; p.out_f32 = out; p.overflow = overflow;
     p.inv_wscale = inv_wscale; p.M = (int)M; p.N_total = N; p.K = K; p.mode = 1; p.n_groups = 1;
     return tc_launch_layer(tm_ah, tm_al, tm_wh, tm_wl, p, cs, leave_free_sms, st);
+}
+
+// y[n, N] = x[n, K] W[N, K]^T + bias (optionally sqrt2 * lrelu) on the tensor cores, fp32-grade (hi/lo split of both operands
+// done here: W per call -- N*K elements, negligible next to the n*N*K product for n >= 128).  N % 256 == 0, K % 64 == 0.
+// Used for BigGAN's generator.gen_z (biggan model.py:211-212,232): [B, 256] x [256, 32768].
+// ws layout: x_hi, x_lo [n*K] fp16 | w_hi, w_lo [N*K] fp16 | {inv_wscale, wscale, absmax} | overflow flag
+size_t tc_linear_workspace_bytes(int64_t n, int N, int K) {
+    return 2 * align_up((size_t)n * K * 2, 256) + 2 * align_up((size_t)N * K * 2, 256) + 512;
+}
+
+int tc_linear(const float *x, const float *w, const float *bias, float *y, int64_t n, int N, int K, bool lrelu, void *ws,
+              cudaStream_t st) {
+    GSB_CHECK_ARG(N % TC_BLOCK_N == 0 && K % TC_BLOCK_K == 0 && n > 0 && n < (1ll << 31) && bias, "tc_linear: need N%%256==0, K%%64==0, bias");
+    if (int r = tc_ensure_attr()) return r;
+    char *p0 = reinterpret_cast<char *>(ws);
+    const size_t xb = align_up((size_t)n * K * 2, 256), wb = align_up((size_t)N * K * 2, 256);
+    __half *x_hi = (__half *)p0, *x_lo = (__half *)(p0 + xb), *w_hi = (__half *)(p0 + 2 * xb), *w_lo = (__half *)(p0 + 2 * xb + wb);
+    float *scal = (float *)(p0 + 2 * xb + 2 * wb);              // inv_wscale, wscale, absmax
+    unsigned *overflow = (unsigned *)(p0 + 2 * xb + 2 * wb + 256);
+    GSB_CHECK_CUDA(cudaMemsetAsync(scal, 0, 512, st));
+    absmax_kernel<<<256, 256, 0, st>>>(w, (int64_t)N * K, scal + 2);
+    GSB_CHECK_LAUNCH();
+    pick_wscale_kernel<<<1, 1, 0, st>>>(scal + 2, scal + 1, scal);
+    GSB_CHECK_LAUNCH();
+    weight_split_kernel<<<1024, 256, 0, st>>>(w, (int64_t)N * K, scal + 1, w_hi, w_lo);
+    GSB_CHECK_LAUNCH();
+    pixelnorm_split_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(x, x_hi, x_lo, n, K, 0, overflow);
+    GSB_CHECK_LAUNCH();
+    CUtensorMap tm_ah, tm_al, tm_wh, tm_wl;
+    if (int r = make_tmap_f16(&tm_ah, x_hi, (uint64_t)n, (uint64_t)K, TC_BLOCK_M)) return r;
+    if (int r = make_tmap_f16(&tm_al, x_lo, (uint64_t)n, (uint64_t)K, TC_BLOCK_M)) return r;
+    if (int r = make_tmap_f16(&tm_wh, w_hi, (uint64_t)N, (uint64_t)K, TC_BLOCK_N)) return r;
+    if (int r = make_tmap_f16(&tm_wl, w_lo, (uint64_t)N, (uint64_t)K, TC_BLOCK_N)) return r;
+    TcParams p;
+    p.bias = bias; p.out_hi = nullptr; p.out_lo = nullptr; p.out_f32 = y; p.overflow = overflow;
+    p.inv_wscale = scal; p.M = (int)n; p.N_total = N; p.K = K; p.mode = lrelu ? 0 : 2; p.n_groups = 1;
+    return tc_launch_layer(tm_ah, tm_al, tm_wh, tm_wl, p, 1, 0, st);
 }
 
 // Full mapping network on the tensor cores.  ws: 4 fp16 buffers of n*dim (two hi/lo ping-pong pairs).

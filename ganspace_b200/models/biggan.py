@@ -75,7 +75,9 @@ class SNLinear(nn.Module):
         return self._eff
 
     def forward(self, x):
-        return _native.linear(x, self.effective_weight(), self.bias.detach())
+        # latents are truncated normals in [-2, 2] * truncation and the class embedding is a fixed vector: inside fp16's range,
+        # so batches of >= 128 rows run on the tensor cores (fp32-grade hi/lo split)
+        return _native.linear(x, self.effective_weight(), self.bias.detach(), bounded=bool(x.abs().max() < 6e4) if x.shape[0] >= 128 else False)
 
 
 class _Generator(nn.Module):
@@ -106,6 +108,7 @@ class AffineLayer:
 
     def __init__(self, Q64, R64, offset64):
         self.Q = Q64                                   # [d, r] fp64, orthonormal columns
+        self.Q32 = Q64.float().contiguous()
         self.R32 = R64.float().contiguous()           # [r, r]
         self.offset = offset64                         # [d] fp64: b + W_eff[:, r:] @ embed
         self.rank = Q64.shape[1]
@@ -116,8 +119,9 @@ class AffineLayer:
         return _native.linear(z, self.R32)
 
     def lift_rows(self, rows64: torch.Tensor) -> torch.Tensor:
-        """rows [k, r] in y-space -> [k, d] in activation space (directions: no offset)."""
-        return rows64 @ self.Q.T
+        """rows [k, r] in y-space -> [k, d] in activation space (directions: no offset); in-tree GEMM kernel, fp32 (the
+        results are stored as float32)."""
+        return _native.linear(rows64.float().contiguous(), self.Q32).double()
 
 
 class BigGAN(BaseModel):
@@ -203,6 +207,8 @@ class BigGAN(BaseModel):
         self.v_class = one_hot.to(self.device)
         self._class_idx = idx
         self._affine = {}
+        if hasattr(self, "model"):
+            self.affine_layer("generator.gen_z")       # thin QR of the folded weight: model/class set-up, not part of a run
 
     def _embed(self) -> torch.Tensor:
         """embeddings(one_hot) = column `idx` of the embedding matrix  -> [128] fp32."""
@@ -222,7 +228,9 @@ class BigGAN(BaseModel):
 
     # ---- low-rank structure of gen_z ----------------------------------------------------------------
     def affine_layer(self, layer_name):
-        if layer_name != "generator.gen_z":
+        # GANSPACE_B200_BIGGAN_AFFINE=0: no low-rank shortcut -- the activations are materialised and go through the general
+        # large-d engine (csrc/bigd.cu), a cross-check of the shortcut
+        if layer_name != "generator.gen_z" or os.environ.get("GANSPACE_B200_BIGGAN_AFFINE", "1") == "0":
             return None
         if layer_name not in self._affine:
             g = self.model.generator.gen_z

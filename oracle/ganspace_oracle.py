@@ -220,6 +220,35 @@ def ipca_partial_fit(st: IPCAState, X: np.ndarray) -> IPCAState:
     return st
 
 
+def ipca_partial_fit_small_side(st: IPCAState, X: np.ndarray) -> IPCAState:
+    """The same partial_fit (_incremental_pca.py:254-380) for d >> rows: the thin SVD of the stacked matrix M [rows, d] through
+    its small-side Gram  M M^T = U S^2 U^T,  Vt = S^-1 U^T M  (fp64) instead of LAPACK gesdd on M -- the same factorisation up to
+    rounding, at rows^2 d instead of rows d min(rows, d) ... with a 30x smaller constant for rows = 2081, d = 32768."""
+    X = np.array(X, copy=True)
+    n_samples = X.shape[0]
+    col_mean, col_var, n_total = incremental_mean_and_var(X, st.mean, st.var, st.n_samples_seen)
+    if st.n_samples_seen == 0:
+        M = X.astype(np.float64) - col_mean
+    else:
+        col_batch_mean = np.mean(X.astype(np.float64), axis=0)
+        mean_correction = np.sqrt((st.n_samples_seen / n_total) * n_samples) * (st.mean - col_batch_mean)
+        M = np.vstack((st.singular_values.reshape((-1, 1)) * st.components, X.astype(np.float64) - col_batch_mean, mean_correction))
+    c = st.n_components
+    lam, U = np.linalg.eigh(M @ M.T)
+    lam, U = lam[::-1][:c], U[:, ::-1][:, :c]
+    S = np.sqrt(np.maximum(lam, 0.0))
+    Vt = (U.T @ M) / S[:, None]
+    Vt, _ = svd_flip_v(Vt)
+    st.explained_variance = S ** 2 / (n_total - 1)
+    st.explained_variance_ratio = S ** 2 / np.sum(col_var * n_total)
+    st.n_samples_seen = n_total
+    st.components = Vt
+    st.singular_values = S
+    st.mean = col_mean
+    st.var = col_var
+    return st
+
+
 def batch_stats(X: np.ndarray):
     """Per-batch sufficient statistics of the Gram-form chain: (n, mean[d], centred Gram[d,d]) in fp64."""
     X64 = X.astype(np.float64)
@@ -306,7 +335,8 @@ def compute_path(sample, activate, latent_dims: int, feat_dims: int, n: int, B: 
     """Restated decomposition.compute (:150-341) for estimator='ipca'.
         sample(seed, B)   -> one model.sample_latent(B) call (latents [B, latent_dims], float32)
         activate(latents) -> the hooked layer's activations flattened to [B, feat_dims]
-    ``ipca``: 'svd' = sklearn-form partial_fit restatement, 'gram' = Gram-chain restatement."""
+    ``ipca``: 'svd' = sklearn-form partial_fit restatement, 'gram' = Gram-chain restatement (d x d), 'small' = small-side
+    restatement (rows x rows; for d >> rows)."""
     d = feat_dims
     c = min(c, d)                                                    # :191
     N, NB, n_lat, K = plan(n, B, c)
@@ -325,6 +355,8 @@ def compute_path(sample, activate, latent_dims: int, feat_dims: int, n: int, B: 
         X = (rows if samples_are_latents else activate(rows)).astype(np.float32).copy()
         if ipca == "svd":
             ipca_partial_fit(st, X)
+        elif ipca == "small":
+            ipca_partial_fit_small_side(st, X)
         else:
             ipca_gram_step(st, *batch_stats(X))
 

@@ -53,3 +53,24 @@ def test_c80_n300k_vs_oracle(oracle, mapping_weights, monkeypatch, mapping):
     cmp = oracle.compare_npz(out, ref)
     assert cmp["min_signed_cos"] >= 0.999 and cmp["max_abs_dvar_ratio"] <= 1e-3, cmp
     assert cmp["act_mean_rel"] < 1e-4 and cmp["lat_stdev_rel"] < 1e-4 and cmp["random_stdevs_rel"] < 1e-4, cmp
+
+
+def test_config3_n100k_vs_oracle(oracle, mapping_weights):
+    """Config 3 (StyleGAN2-car, Z space, layer=style + latent regression) at N = 100k against the oracle."""
+    import tempfile
+    from types import SimpleNamespace
+    from ganspace_b200.config import Config
+    from ganspace_b200.decomposition import compute_arrays
+    from ganspace_b200.models import get_instrumented_model, StyleGAN2
+    ws, bs = mapping_weights
+    ref = oracle.compute_stylegan2_style(ws, bs, 100_000, 10_000, 80, False)
+    dev = torch.device("cuda:0")
+    model = StyleGAN2(dev, "car", random_init=1234)
+    inst = get_instrumented_model("StyleGAN2", "car", "style", dev, model=model, use_w=False)
+    cfg = Config(model="StyleGAN2", layer="style", output_class="car", components=80, n=100_000, batch_size=10_000,
+                 use_w=False, estimator="ipca")
+    out = compute_arrays(cfg, inst)
+    cmp = oracle.compare_npz(out, ref)
+    assert cmp["min_signed_cos"] >= 0.999 and cmp["min_lat_signed_cos"] >= 0.999 and cmp["max_abs_dvar_ratio"] <= 1e-3, cmp
+    assert cmp["act_mean_rel"] < 1e-4 and cmp["act_stdev_rel"] < 1e-4 and cmp["random_stdevs_rel"] < 1e-4, cmp
+    inst.close()

@@ -137,3 +137,17 @@ def test_conv_layer_pca_restatement_vs_reference(oracle, golden, mapping_weights
     assert np.allclose(out["act_stdev"], g["act_stdev"], rtol=1e-4)
     assert np.allclose(out["act_mean"].reshape(-1), g["act_mean"].reshape(-1), atol=1e-5)
     assert np.allclose(out["random_stdevs"], g["random_stdevs"], rtol=1e-4)
+
+
+def test_small_side_restatement_equals_svd_form(oracle):
+    """ipca_partial_fit_small_side (used for d >> rows, config 4 at N = 100k) is the same factorisation as the gesdd form."""
+    rng = np.random.RandomState(3)
+    basis = rng.standard_normal((600, 24)) * (0.8 ** np.arange(24))[None, :]
+    a, b = oracle.IPCAState(6), oracle.IPCAState(6)
+    for k in range(3):
+        X = (rng.standard_normal((50, 24)) @ basis.T + 0.05 * rng.standard_normal((50, 600)) + 1.5).astype(np.float32)
+        oracle.ipca_partial_fit(a, X)
+        oracle.ipca_partial_fit_small_side(b, X)
+    assert np.sum(a.components * b.components, axis=1).min() > 1 - 1e-6
+    assert np.allclose(a.singular_values, b.singular_values, rtol=1e-5)
+    assert np.allclose(a.explained_variance_ratio, b.explained_variance_ratio, rtol=1e-5) and np.allclose(a.mean, b.mean)
