@@ -235,3 +235,43 @@ def test_mt19937_jump_polynomials_match_numpy_state():
         rs.randint(0, 2 ** 32, size=step * j, dtype=np.uint32)          # one word per draw
         _, key, pos = rs.get_state()[:3]
         assert pos == 624 and np.array_equal(key[1:], st[1:]) and (key[0] >> 31) == (st[0] >> 31)
+
+
+def test_named_direction_pkl_round_trip_and_reference_file(tmp_path):
+    """The named-direction .pkl format (interactive.py:88-127, 526-571): the file the reference ships loads through
+    load_named_components; a direction exported from an .npz has the reference's keys, value types and file name."""
+    import pickle
+    from ganspace_b200 import directions
+    from ganspace_b200.config import Config
+    ref_file = Path(__file__).parent / "golden" / "ref_named_direction.pkl"      # the reference's shipped artefact (data fixture)
+    with open(ref_file, "rb") as f:
+        ref = pickle.load(f)
+    assert set(directions.KEYS) <= set(ref)
+    d = tmp_path / "dirs"
+    d.mkdir()
+    (d / "StyleGAN2-Light_direction-ffhq-ipca-w-style-comp15-range8-9.pkl").write_bytes(ref_file.read_bytes())
+    comp = directions.load_named_components(str(d), "StyleGAN2", "ffhq", "W")
+    assert comp.names == ["Light direction: 15 (8-8)"] or comp.names[0].endswith("15 (8-8)")
+    assert comp.ranges == [(8, 9)] and comp.latent_types == ["W"] and comp.layer_names == ["style"]
+    assert comp.Z_comp[0].shape == (1, 512) and abs(comp.Z_stdev[0] - ref["lat_stdev"]) == 0
+    with pytest.raises(RuntimeError, match="No valid components"):
+        directions.load_named_components(str(d), "StyleGAN2", "car", "W")
+    # export from an .npz and read it back
+    rng = np.random.RandomState(0)
+    arrays = {"act_comp": rng.standard_normal((4, 1, 512)).astype(np.float32), "act_mean": np.zeros((1, 512), np.float32),
+              "act_stdev": rng.rand(4).astype(np.float32), "lat_comp": rng.standard_normal((4, 1, 512)).astype(np.float32),
+              "lat_mean": np.zeros((1, 512), np.float32), "lat_stdev": rng.rand(4).astype(np.float32),
+              "var_ratio": rng.rand(4).astype(np.float32), "random_stdevs": rng.rand(4).astype(np.float32)}
+    npz = tmp_path / "c.npz"
+    np.savez(npz, **arrays)
+    cfg = Config(model="StyleGAN2", layer="style", output_class="ffhq", components=4, n=1000, use_w=True, estimator="ipca")
+    out = directions.export_direction(npz, d, cfg, 2, "Light direction", "W", 8, 9, sigma_range=2.5, truncation=0.9, example_seed=7)
+    assert out.name == "StyleGAN2-Light_direction-ffhq-ipca-w-style-comp2-range8-9.pkl"
+    with open(out, "rb") as f:
+        mine = pickle.load(f)
+    for k in directions.KEYS:
+        assert type(mine[k]) is type(ref[k]) or (k == "sigma_range" and isinstance(mine[k], float)), k
+    assert mine["act_comp"].shape == ref["act_comp"].shape and mine["act_comp"].dtype == ref["act_comp"].dtype
+    assert set(mine["decomposition"]) == set(ref["decomposition"])
+    comp2 = directions.load_named_components(str(d), "StyleGAN2", "ffhq", "W")
+    assert len(comp2.names) == 2 and np.array_equal(comp2.Z_comp[1], arrays["lat_comp"][2])       # sorted: comp15 < comp2
