@@ -230,8 +230,9 @@ class StyleGAN2(BaseModel):
                     events.append(ev)
             for side in sides:
                 z.record_stream(side)
+                seeds_dev.record_stream(side)          # read by launches that run long after this function has returned
         packed = self.model.style.packed() if self.w_primary else None
-        state = {"g": 0}
+        state = {"g": 0, "keep": seeds_dev}
         free_sms = int(os.environ.get("GANSPACE_B200_LAZY_FREE_SMS", 72 if parts > 1 else 48))
 
         def ensure(row_end):
