@@ -178,12 +178,14 @@ def test_large_d_chain_vs_sklearn_form(oracle, monkeypatch, d, nb, c, k, gram):
     assert np.sum(np.asarray(comp, np.float64) * st.components, axis=1).min() > 1 - 1e-5
 
 
-def _run_layer(layer, n, b, c):
+def _run_layer(layer, n, b, c, perturb=None):
     from ganspace_b200.config import Config
     from ganspace_b200.decomposition import get_or_compute
     from ganspace_b200.models import get_instrumented_model, StyleGAN2
     dev = torch.device("cuda:0")
     model = StyleGAN2(dev, "ffhq", random_init=1234)
+    if perturb:
+        _perturb(model.model, perturb)
     inst = get_instrumented_model("StyleGAN2", "ffhq", layer, dev, model=model, use_w=False)
     cfg = Config(model="StyleGAN2", layer=layer, output_class="ffhq", components=c, n=n, batch_size=b, use_w=False,
                  estimator="ipca")
@@ -214,4 +216,35 @@ def test_conv_layer_pca_vs_reference_golden(golden, oracle, fixture, layer, n, b
     assert cmp["min_signed_cos"] >= COS_TOL, cmp
     assert cmp["max_abs_dvar_ratio"] <= RATIO_TOL, cmp
     assert cmp["min_lat_signed_cos"] >= COS_TOL, cmp
+    assert cmp["act_mean_rel"] < 1e-3 and cmp["act_stdev_rel"] < 1e-3 and cmp["random_stdevs_rel"] < 1e-3, cmp
+
+
+def test_conv_layer_pca_nonzero_noise_vs_reference_golden(golden, oracle):
+    """End to end with NON-ZERO NoiseInjection weights and activation biases (both are 0 at random init, which leaves the noise
+    path of the fused epilogue untested at the PCA level): layer=convs.1, Z space + regression, against the reference's .npz
+    (oracle/gen_golden_r2.py G10; fixed noise maps from set_noise_seed(0) on the CPU generator, as the reference's CPU run)."""
+    g = golden("c5n_stylegan2_ffhq_convs1_z_noise_n4000_b500_c8.npz")
+    out, name = _run_layer("convs.1", 4000, 500, 8, perturb=[str(x) for x in g["perturbed"]])
+    assert name == str(g["dump_name"])
+    cmp = oracle.compare_npz(out, g)
+    assert cmp["min_signed_cos"] >= COS_TOL and cmp["max_abs_dvar_ratio"] <= RATIO_TOL and cmp["min_lat_signed_cos"] >= COS_TOL, cmp
+    assert cmp["act_mean_rel"] < 1e-3 and cmp["act_stdev_rel"] < 1e-3 and cmp["random_stdevs_rel"] < 1e-3, cmp
+    # the perturbation matters: the zero-noise fixture of the same layer has a different mean
+    g0 = golden("c5s_stylegan2_ffhq_convs1_z_n4000_b500_c8.npz")
+    assert np.abs(g["act_mean"] - g0["act_mean"]).max() > 1e-2
+
+
+def test_config5_layer_convs4_vs_reference_golden(golden, oracle):
+    """BASELINE config 5's layer itself: convs.4 (d = 524288), Z space + regression, N = 4000, through the large-d engine with
+    the tensor-core Gram, against the unmodified reference (oracle/gen_golden_r2.py G9; act_comp stored as float16)."""
+    from conftest import GOLDEN
+    fixture = "c5_stylegan2_ffhq_convs4_z_n4000_b500_c4.npz"
+    if not (GOLDEN / fixture).exists():
+        pytest.skip(f"fixture {fixture} not generated")
+    g = dict(golden(fixture))
+    g["act_comp"] = g.pop("act_comp_f16").astype(np.float32)
+    out, name = _run_layer("convs.4", 4000, 500, 4)
+    assert name == str(g["dump_name"]) and out["act_comp"].shape == (4, 1, 512, 32, 32)
+    cmp = oracle.compare_npz(out, g)
+    assert cmp["min_signed_cos"] >= COS_TOL and cmp["max_abs_dvar_ratio"] <= RATIO_TOL and cmp["min_lat_signed_cos"] >= COS_TOL, cmp
     assert cmp["act_mean_rel"] < 1e-3 and cmp["act_stdev_rel"] < 1e-3 and cmp["random_stdevs_rel"] < 1e-3, cmp
