@@ -436,6 +436,12 @@ def compute_arrays(config, instrumented_model, state=None):
                         if pending is not None and not exchange.finish(pending, transformer, NB):
                             stop = True
                         pending = cur
+                        if rnd[0] < 2 * world * STATS_BLOCK and not stop:
+                            # the first rounds are merged at once (the chain is idle and waiting for them); later rounds one
+                            # round late, so that the collective overlaps the next round's kernels
+                            if not exchange.finish(pending, transformer, NB):
+                                stop = True
+                            pending = None
                 if pending is not None and not stop and not exchange.finish(pending, transformer, NB):
                     stop = True
             ensure_rows(lat.shape[0])
