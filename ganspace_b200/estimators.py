@@ -33,7 +33,8 @@ class DeviceIncrementalPCA:
         self.batch_size = batch_size
         self._device = device
         self._chain = None
-        self._host = None            # cached export
+        self._host = None            # cached export (host view)
+        self._dev = None             # ... and its device tensors
         self._shard = None           # (rank, world): feature-sharded large-d engine
         self._stage = None
         self.n_samples_seen_ = np.int64(0)
@@ -162,13 +163,32 @@ class DeviceIncrementalPCA:
 
     # -- sklearn attribute names (host copies, fetched lazily) ---------------------------------------
     def device_attributes(self):
-        return self._chain.export()
+        """sklearn's fitted attributes as device tensors; one export per fit state (the host view below reuses it)."""
+        if self._chain is None:
+            raise AttributeError("IncrementalPCA is not fitted yet")
+        if self._host is None or self._dev is None:
+            self._dev = self._chain.export()
+        return self._dev
 
     def _export(self):
         if self._chain is None:
             raise AttributeError("IncrementalPCA is not fitted yet")
         if self._host is None:
-            self._host = {k: v.cpu().numpy() for k, v in self._chain.export().items()}
+            dev = self._chain.export()
+            # ONE device->host transfer: the six arrays packed into one fp64 buffer (each .cpu() is a synchronising copy)
+            keys = list(dev)
+            if sum(dev[k].numel() for k in keys) <= (1 << 22):
+                flat = torch.cat([dev[k].reshape(-1).double() for k in keys]).cpu().numpy()
+                host, off = {}, 0
+                for k in keys:
+                    n = dev[k].numel()
+                    host[k] = flat[off:off + n].reshape(tuple(dev[k].shape)).astype(
+                        np.float32 if dev[k].dtype == torch.float32 else np.float64)
+                    off += n
+            else:                                        # conv feature maps: 168 MB of components, copied as they are
+                host = {k: v.cpu().numpy() for k, v in dev.items()}
+            self._dev = dev
+            self._host = host
         return self._host
 
     components_ = property(lambda self: self._export()["components"])
