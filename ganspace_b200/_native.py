@@ -67,6 +67,8 @@ SIGNATURES = {
     "gsb_synthesis_workspace_bytes": (_Z, [_P, _I, _L]),
     "gsb_synthesis_forward": (_I, [_P, _P, _I, _I, _I, _P, _L, _P, _L, _P, _Z, _P]),
     "gsb_synthesis_status": (_I, [_P, _P, _I, _I, _P]),
+    "gsb_synthesis_render_workspace_bytes": (_Z, [_P, _I, _L, _I]),
+    "gsb_synthesis_render": (_I, [_P, _P, _I, _I, _I, _P, _I, _P, _I, _L, _P, _L, _P, _P, _Z, _P]),
     "gsb_bigd_rows": (_I, [_I, _I]),
     "gsb_bigd_state_bytes": (_Z, [_L, _I]),
     "gsb_bigd_workspace_bytes": (_Z, [_L, _I, _I, _I]),
@@ -85,6 +87,12 @@ class StyledConvDesc(C.Structure):
     _fields_ = [("conv_weight", C.c_void_p), ("mod_weight", C.c_void_p), ("mod_bias", C.c_void_p),
                 ("act_bias", C.c_void_p), ("noise", C.c_void_p), ("noise_weight", C.c_void_p),
                 ("cin", C.c_int), ("cout", C.c_int), ("upsample", C.c_int), ("res_in", C.c_int)]
+
+
+class ToRGBDesc(C.Structure):
+    """``gsb_to_rgb`` of include/ganspace_b200.h."""
+    _fields_ = [("conv_weight", C.c_void_p), ("mod_weight", C.c_void_p), ("mod_bias", C.c_void_p), ("bias", C.c_void_p),
+                ("cin", C.c_int)]
 
 
 class NativeError(RuntimeError):
@@ -771,6 +779,43 @@ class PackedSynthesis:
         instrument.count(launches)
         instrument.add_rows("synthesis", n)
         return out
+
+    def render(self, w_layers: torch.Tensor, n_run: int, rgbs, want_act: bool = False):
+        """Generator.forward on the fused chain (gsb_synthesis_render): ``w_layers`` [Lw, n, style_dim] per-layer latents (Lw = 1:
+        one global latent), ``rgbs``: list of dicts (conv_weight [3,cin], mod_weight, mod_bias, bias [3]) for to_rgb1,
+        to_rgbs.0, ... up to the one that follows layer n_run-1 or earlier.  Returns (activation of layer n_run-1 as fp32 NHWC
+        rows or None, skip image after the last ToRGB as fp32 NHWC [n, res, res, 3] or None)."""
+        lib = load()
+        assert w_layers.is_cuda and w_layers.dtype == torch.float32 and w_layers.dim() == 3 and w_layers.shape[2] == self.style_dim
+        w_layers = w_layers.contiguous()
+        Lw, n = int(w_layers.shape[0]), int(w_layers.shape[1])
+        keep = []
+        descs = (ToRGBDesc * max(1, len(rgbs)))()
+        for j, r in enumerate(rgbs):
+            ts = {k: r[k].detach().to(self.device, torch.float32).contiguous() for k in ("conv_weight", "mod_weight", "mod_bias", "bias")}
+            keep.append(ts)
+            cin = ts["conv_weight"].shape[-1]
+            assert ts["conv_weight"].numel() == 3 * cin and ts["bias"].numel() == 3
+            for k, t in ts.items():
+                setattr(descs[j], k, t.data_ptr())
+            descs[j].cin = int(cin)
+        act = rgb = None
+        if want_act:
+            act = torch.empty((n, self.out_dims(n_run)), dtype=torch.float32, device=self.device)
+        if rgbs:
+            res = self.shapes[2 * (len(rgbs) - 1)][0]
+            rgb = torch.empty((n, res, res, 3), dtype=torch.float32, device=self.device)
+        ws_bytes = lib.gsb_synthesis_render_workspace_bytes(self.desc, n_run, n, self.style_dim)
+        ws = scratch.get("synthesis", ws_bytes, self.device)
+        with torch.cuda.device(self.device), instrument.section("synthesis"):
+            _check(lib.gsb_synthesis_render(_ptr(self.packed), self.desc, self.n_layers, n_run, self.style_dim, descs, len(rgbs),
+                                            _ptr(w_layers), Lw, n, _ptr(act), act.stride(0) if act is not None else 0, _ptr(rgb),
+                                            _ptr(ws), ws.numel(), _stream()), "gsb_synthesis_render")
+            if keep:
+                torch.cuda.current_stream().synchronize()      # the temporary parameter copies may be freed after this
+        instrument.count(1)
+        instrument.add_rows("synthesis", n)
+        return act, rgb
 
     def check(self):
         flags = C.c_uint(0)

@@ -184,8 +184,10 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m_tiles = (p.M + TC_BLOCK_M - 1) / TC_BLOCK_M;
-    const int num_n_tiles = p.N_total / TC_BLOCK_N;
-    const int num_k_blocks = p.K / TC_BLOCK_K;
+    // N and K need not be multiples of the tile: the TMA unit zero-fills operand rows / columns past the tensor's extent and
+    // clips stores (the 128/64/32-channel StyledConv blocks: N = 9 cout = 1152 / 576 / 288, K = cin down to 32)
+    const int num_n_tiles = (p.N_total + TC_BLOCK_N - 1) / TC_BLOCK_N;
+    const int num_k_blocks = (p.K + TC_BLOCK_K - 1) / TC_BLOCK_K;
     // cluster of cs CTAs along M (cs = 1: no cluster): CTA `crank` of cluster `cluster_id` owns row tile ct * cs + crank of every
     // cluster tile ct it visits; all CTAs of a cluster run the same number of pipeline steps (row tiles past the end are
     // zero-filled by the TMA unit and never stored)
@@ -322,8 +324,8 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
                 }
                 if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging has been read out
                 if (c0 == 0 && p.mode != 1) {                      // (safe: the previous tile's readers passed a barrier below)
-                    bias_s[et] = __ldg(&p.bias[n0 + et]);
-                    bias_s[et + 128] = __ldg(&p.bias[n0 + et + 128]);
+                    bias_s[et] = (n0 + et < p.N_total) ? __ldg(&p.bias[n0 + et]) : 0.f;
+                    bias_s[et + 128] = (n0 + et + 128 < p.N_total) ? __ldg(&p.bias[n0 + et + 128]) : 0.f;
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 float f[64];
@@ -363,10 +365,10 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the TMA unit
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (storer && !(p.dbg & 1)) {
+                if (storer && !(p.dbg & 1) && n0 + c0 < p.N_total) {
                     if (to_f32) {
                         tma_store_2d(&tm_o0, stg, n0 + c0, m0);
-                        tma_store_2d(&tm_o0, stg + TC_A_BYTES, n0 + c0 + 32, m0);
+                        if (n0 + c0 + 32 < p.N_total) tma_store_2d(&tm_o0, stg + TC_A_BYTES, n0 + c0 + 32, m0);
                     } else {
                         tma_store_2d(&tm_o0, stg, n0 + c0, m0);
                         tma_store_2d(&tm_o1, stg + TC_A_BYTES, n0 + c0, m0);
@@ -479,7 +481,8 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D fp16 row-major [rows, cols] tensor, box = box_rows x 64 columns, 128B swizzle
+// 2-D fp16 row-major [rows, cols] tensor, box = box_rows x 64 columns, 128B swizzle (rows / cols smaller than the box are fine:
+// the TMA unit fills the rest of the box with zeros)
 static int make_tmap_f16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return GSB_ERR_CUDA; }
@@ -603,7 +606,7 @@ static int tc_launch_layer(const CUtensorMap &tm_ah, const CUtensorMap &tm_al, c
         if (int r = make_tmap_f16(&tm_o0, p.out_hi, (uint64_t)p.M, (uint64_t)p.N_total, TC_BLOCK_M)) return r;
         if (int r = make_tmap_f16(&tm_o1, p.out_lo, (uint64_t)p.M, (uint64_t)p.N_total, TC_BLOCK_M)) return r;
     }
-    const int m_tiles = (p.M + TC_BLOCK_M - 1) / TC_BLOCK_M, n_tiles = p.N_total / TC_BLOCK_N;
+    const int m_tiles = (p.M + TC_BLOCK_M - 1) / TC_BLOCK_M, n_tiles = (p.N_total + TC_BLOCK_N - 1) / TC_BLOCK_N;
     const int num_ct = (m_tiles + cs - 1) / cs;
     int avail = (num_sms() - leave_free_sms) / cs;
     if (avail < 16 / cs) avail = 16 / cs;
@@ -632,8 +635,8 @@ static int tc_launch_layer(const CUtensorMap &tm_ah, const CUtensorMap &tm_al, c
 // Used by the modulated-convolution path (synthesis.cu): one dense contraction per 3x3 tap.
 int tc_gemm_plain(const __half *a_hi, const __half *a_lo, int64_t M, int K, const __half *w_hi, const __half *w_lo, int N,
                   const float *inv_wscale, float *out, unsigned *overflow, int leave_free_sms, cudaStream_t st) {
-    GSB_CHECK_ARG(N % TC_BLOCK_N == 0 && K % TC_BLOCK_K == 0 && M > 0 && M < (1ll << 31),
-                  "tc_gemm_plain: need N%%256==0, K%%64==0 (M=%lld N=%d K=%d)", (long long)M, N, K);
+    GSB_CHECK_ARG(N % 32 == 0 && N >= 32 && K % 8 == 0 && K >= 8 && M > 0 && M < (1ll << 31),
+                  "tc_gemm_plain: need N%%32==0, K%%8==0 (M=%lld N=%d K=%d)", (long long)M, N, K);
     if (int r = tc_ensure_attr()) return r;
     // few row tiles (a chunk of a conv layer): no cluster, one output tile per work unit; many: weight multicast
     const int m_tiles = (int)((M + TC_BLOCK_M - 1) / TC_BLOCK_M);

@@ -82,9 +82,9 @@ static int check_layers(const gsb_styled_conv *layers, int n_layers, int style_d
     GSB_CHECK_ARG(style_dim > 0 && style_dim % 16 == 0, "synthesis: style_dim %% 16");
     for (int l = 0; l < n_layers; ++l) {
         const gsb_styled_conv &c = layers[l];
-        GSB_CHECK_ARG(c.cin % 128 == 0 && c.cout % 256 == 0, "synthesis: layer %d needs cin%%128==0, cout%%256==0 (cin=%d cout=%d)", l, c.cin,
-                      c.cout);
-        GSB_CHECK_ARG(c.res_in >= 4 && c.res_in <= 512, "synthesis: layer %d bad res_in", l);
+        GSB_CHECK_ARG(c.cin % 32 == 0 && c.cout % 32 == 0 && c.cin >= 32 && c.cout >= 32,
+                      "synthesis: layer %d needs cin%%32==0, cout%%32==0 (cin=%d cout=%d)", l, c.cin, c.cout);
+        GSB_CHECK_ARG(c.res_in >= 4 && c.res_in <= 1024, "synthesis: layer %d bad res_in", l);
         if (l == 0) GSB_CHECK_ARG(c.res_in == 4 && !c.upsample, "synthesis: layer 0 is conv1 on the 4x4 constant");
         else GSB_CHECK_ARG(c.cin == layers[l - 1].cout && c.res_in == res_out_of(layers[l - 1]), "synthesis: layer %d does not chain", l);
     }
@@ -186,6 +186,32 @@ __global__ void sy_const_modulate_kernel(const float *__restrict__ cst, const fl
     if (ovf) atomicOr(overflow, 1u);
 }
 
+// y[n, N] = x[n, K] W[N, K]^T + bias: one thread per output, for the style / demodulation products of blocks whose channel
+// count is below the GEMM kernels' 128-wide tiles (64- and 32-channel blocks at 512^2 / 1024^2)
+__global__ void sy_small_linear_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+                                       float *__restrict__ y, int64_t n, int N, int K) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n * N) return;
+    const int j = (int)(idx % N);
+    const int64_t r = idx / N;
+    const float *xr = x + r * K, *wr = w + (int64_t)j * K;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = 0;
+    for (; k + 3 < K; k += 4) {
+        const float4 xv = *reinterpret_cast<const float4 *>(xr + k), wv = *reinterpret_cast<const float4 *>(wr + k);
+        a0 = fmaf(xv.x, wv.x, a0); a1 = fmaf(xv.y, wv.y, a1); a2 = fmaf(xv.z, wv.z, a2); a3 = fmaf(xv.w, wv.w, a3);
+    }
+    for (; k < K; ++k) a0 = fmaf(xr[k], wr[k], a0);
+    y[idx] = (a0 + a1) + (a2 + a3) + bias[j];
+}
+static int sy_linear(const float *x, const float *w, const float *bias, float *y, int64_t n, int N, int K, gsb_stream_t stream) {
+    if (N % 128 == 0 && K % 16 == 0) return gsb_linear_forward(x, w, bias, y, n, N, K, 0, nullptr, 0, stream);
+    const int64_t total = n * N;
+    sy_small_linear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, n, N, K);
+    GSB_CHECK_LAUNCH();
+    return GSB_OK;
+}
+
 struct EpiParams {
     const float *demod;     // [nb, c]  (chunk-local rows)
     const float *noise;     // [H*W] pre-multiplied by NoiseInjection.weight
@@ -195,6 +221,11 @@ struct EpiParams {
     float *out_f32;         // hooked layer: row b at out_f32 + b*ld
     int64_t ld;
     unsigned *overflow;
+    // ToRGB of this resolution (model.py:344-363), fused: rgb[b,pix,o] += sum_c (scale W)[o,c] s_rgb[b,c] f[b,pix,c]
+    const float *rgb_w;     // [3, c] ToRGB.conv.weight (unscaled), or nullptr
+    const float *rgb_s;     // [nb, c] ToRGB style (chunk-local rows)
+    float *rgb_out;         // [nb, H*W, 3] (chunk-local), pre-initialised with bias + up-sampled skip
+    float rgb_scale;        // 1 / sqrt(c)
 };
 // conv result (4 channels) -> demod, noise, bias, leaky-ReLU * sqrt2 -> next layer's operand or the fp32 activation
 __device__ __forceinline__ void sy_epilogue(const EpiParams &e, float4 acc, int64_t b, int pix, int hw, int c, int q) {
@@ -206,15 +237,64 @@ __device__ __forceinline__ void sy_epilogue(const EpiParams &e, float4 acc, int6
     const float sqrt2 = 1.41421356237309515f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) f[k] = sqrt2 * ((f[k] >= 0.f) ? f[k] : 0.2f * f[k]);
+    if (e.rgb_w) {
+        // the channel quads of one pixel sit in consecutive lanes (c/4 of them, a power of two; >= 32: whole warps)
+        const float4 sr = *reinterpret_cast<const float4 *>(e.rgb_s + b * c + 4 * q);
+        const float g[4] = {f[0] * sr.x, f[1] * sr.y, f[2] * sr.z, f[3] * sr.w};
+        float r[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            const float4 wv = *reinterpret_cast<const float4 *>(e.rgb_w + (int64_t)o * c + 4 * q);
+            r[o] = e.rgb_scale * (g[0] * wv.x + g[1] * wv.y + g[2] * wv.z + g[3] * wv.w);
+        }
+        const int cq = c >> 2, span = cq < 32 ? cq : 32;
+        for (int off = span >> 1; off > 0; off >>= 1) {
+#pragma unroll
+            for (int o = 0; o < 3; ++o) r[o] += __shfl_xor_sync(0xffffffffu, r[o], off);
+        }
+        if ((q & (span - 1)) == 0) {
+            float *dst = e.rgb_out + (b * hw + pix) * 3;
+            atomicAdd(dst, r[0]); atomicAdd(dst + 1, r[1]); atomicAdd(dst + 2, r[2]);
+        }
+    }
     if (e.s_next) {
         const float4 sn = *reinterpret_cast<const float4 *>(e.s_next + b * c + 4 * q);
         f[0] *= sn.x; f[1] *= sn.y; f[2] *= sn.z; f[3] *= sn.w;
         bool ovf = false;
         store_split4(f, e.out_hi, e.out_lo, (b * hw + pix) * (int64_t)c + 4 * q, ovf);
         if (ovf) atomicOr(e.overflow, 1u);
-    } else {
+    } else if (e.out_f32) {
         *reinterpret_cast<float4 *>(e.out_f32 + b * e.ld + (int64_t)pix * c + 4 * q) = make_float4(f[0], f[1], f[2], f[3]);
     }
+}
+
+// rgb[b, y, x, o] = bias[o] (+ Upsample(prev)[b, y, x, o]):  upfirdn2d(prev, [1,3,3,1] outer * 4 / 64, up = 2, pad = (2, 1))
+// (model.py:33-51, op/upfirdn2d.py:157-198): zero-insertion puts prev[i] at 2i; out[y] = sum_i k[i] up[y + i - 2].
+__global__ void sy_rgb_init_kernel(const float *__restrict__ bias, const float *__restrict__ prev, int64_t n, int R, float *__restrict__ rgb) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= n * R * R) return;
+    const int x = (int)(idx % R), y = (int)((idx / R) % R);
+    const int64_t b = idx / ((int64_t)R * R);
+    float acc[3] = {bias[0], bias[1], bias[2]};
+    if (prev) {
+        const int Rp = R >> 1;
+        const float k1[4] = {1.f, 3.f, 3.f, 1.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int u = y + i - 2;
+            if (u < 0 || (u & 1) || (u >> 1) >= Rp) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int v = x + j - 2;
+                if (v < 0 || (v & 1) || (v >> 1) >= Rp) continue;
+                const float kw = k1[i] * k1[j] * 0.0625f;
+                const float *pp = prev + ((b * Rp + (u >> 1)) * Rp + (v >> 1)) * 3;
+                acc[0] = fmaf(kw, pp[0], acc[0]); acc[1] = fmaf(kw, pp[1], acc[1]); acc[2] = fmaf(kw, pp[2], acc[2]);
+            }
+        }
+    }
+    float *o = rgb + idx * 3;
+    o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
 }
 
 // stride-1 3x3: gather the nine tap planes.  Y [nb*H*W, 9*c]
@@ -305,13 +385,14 @@ struct SynthWs {
     float *s2;
     __half *act[2][2];     // [ping-pong][hi/lo]
     float *Y, *T;
+    float *rgb[2], *rgb_s, *rgb_modw;      // render path: skip images (ping-pong), ToRGB style, scaled modulation weight
     size_t bytes;
 };
 static int chunk_samples(const gsb_styled_conv &c) {
     int spc = SY_CHUNK_ROWS / (c.res_in * c.res_in);
     return spc < 1 ? 1 : spc;
 }
-static SynthWs synth_ws(void *base, const gsb_styled_conv *layers, int n_run, int64_t n) {
+static SynthWs synth_ws(void *base, const gsb_styled_conv *layers, int n_run, int64_t n, bool with_rgb = false, int style_dim = 0) {
     SynthWs w;
     char *p = reinterpret_cast<char *>(base);
     size_t off = 0;
@@ -337,6 +418,15 @@ static SynthWs synth_ws(void *base, const gsb_styled_conv *layers, int n_run, in
         for (int h = 0; h < 2; ++h) w.act[a][h] = (__half *)take(act_elems * 2);
     w.Y = (float *)take(y_elems * 4);
     w.T = (float *)take((t_elems ? t_elems : 64) * 4);
+    w.rgb[0] = w.rgb[1] = w.rgb_s = w.rgb_modw = nullptr;
+    if (with_rgb) {
+        const int ro = res_out_of(layers[n_run - 1]);
+        size_t cm = 0;
+        for (int l = 0; l < n_run; ++l) cm = cm > (size_t)layers[l].cout ? cm : (size_t)layers[l].cout;
+        for (int a = 0; a < 2; ++a) w.rgb[a] = (float *)take((size_t)n * ro * ro * 3 * 4);
+        w.rgb_s = (float *)take((size_t)n * cm * 4);
+        w.rgb_modw = (float *)take(cm * (size_t)style_dim * 4);
+    }
     w.bytes = off;
     return w;
 }
@@ -391,30 +481,35 @@ extern "C" size_t gsb_synthesis_workspace_bytes(const gsb_styled_conv *layers, i
     return gsb::synth_ws(nullptr, layers, n_run, n).bytes;
 }
 
-extern "C" int gsb_synthesis_forward(const void *d_packed, const gsb_styled_conv *layers, int n_layers, int n_run, int style_dim,
-                                     const float *d_w, int64_t n, float *d_out, int64_t ld_out, void *d_workspace,
-                                     size_t workspace_bytes, gsb_stream_t stream) {
-    using namespace gsb;
+namespace gsb {
+
+// layers[0 .. n_run) on per-layer latents d_w [w_layers][n][style_dim] (layer l reads entry min(l, w_layers - 1)); optional fp32
+// activation of the last layer (d_out), optional ToRGB chain: rgbs[j] follows layer 2j and reads latent entry 2j + 1.
+static int synthesis_run(const void *d_packed, const gsb_styled_conv *layers, int n_layers, int n_run, int style_dim,
+                         const gsb_to_rgb *rgbs, int n_rgb, const float *d_w, int w_layers, int64_t n, float *d_out, int64_t ld_out,
+                         float *d_rgb_out, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
     if (int r = check_layers(layers, n_layers, style_dim)) return r;
-    GSB_CHECK_ARG(d_packed && d_w && d_out && d_workspace, "synthesis_forward: null pointer");
-    GSB_CHECK_ARG(n_run >= 1 && n_run <= n_layers, "synthesis_forward: n_run out of range");
+    GSB_CHECK_ARG(d_packed && d_w && d_workspace && (d_out || d_rgb_out), "synthesis: null pointer");
+    GSB_CHECK_ARG(n_run >= 1 && n_run <= n_layers && w_layers >= 1, "synthesis: n_run / w_layers out of range");
+    GSB_CHECK_ARG(n_rgb >= 0 && (n_rgb == 0 || (rgbs && d_rgb_out && 2 * (n_rgb - 1) <= n_run - 1)), "synthesis: bad ToRGB list");
     if (n == 0) return GSB_OK;
     const gsb_styled_conv &last = layers[n_run - 1];
     const int ro_last = res_out_of(last);
-    GSB_CHECK_ARG(n > 0 && ld_out >= (int64_t)ro_last * ro_last * last.cout && ld_out % 4 == 0, "synthesis_forward: bad n / ld_out");
+    GSB_CHECK_ARG(n > 0 && (!d_out || (ld_out >= (int64_t)ro_last * ro_last * last.cout && ld_out % 4 == 0)), "synthesis: bad n / ld_out");
     SynthView v = synth_view(const_cast<void *>(d_packed), layers, n_layers, style_dim);
-    SynthWs w = synth_ws(d_workspace, layers, n_run, n);
-    if (workspace_bytes < w.bytes) { set_error("synthesis_forward: workspace too small (%zu < %zu)", workspace_bytes, w.bytes); return GSB_ERR_WORKSPACE; }
+    SynthWs w = synth_ws(d_workspace, layers, n_run, n, n_rgb > 0, style_dim);
+    if (workspace_bytes < w.bytes) { set_error("synthesis: workspace too small (%zu < %zu)", workspace_bytes, w.bytes); return GSB_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
+    auto latent = [&](int idx) { return d_w + (size_t)(idx < w_layers ? idx : w_layers - 1) * n * style_dim; };
 
     // styles and demodulation factors of every layer that runs (model.py:234,239)
     for (int l = 0; l < n_run; ++l) {
         const gsb_styled_conv &c = layers[l];
-        if (int r = gsb_linear_forward(d_w, v.L[l].modw, v.L[l].modb, w.S[l], n, c.cin, style_dim, 0, nullptr, 0, stream)) return r;
+        if (int r = sy_linear(latent(l), v.L[l].modw, v.L[l].modb, w.S[l], n, c.cin, style_dim, stream)) return r;
         const int64_t cnt = n * c.cin;
         sy_square_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(w.S[l], cnt, w.s2);
         GSB_CHECK_LAUNCH();
-        if (int r = gsb_linear_forward(w.s2, v.L[l].wsq, v.zeros, w.D[l], n, c.cout, c.cin, 0, nullptr, 0, stream)) return r;
+        if (int r = sy_linear(w.s2, v.L[l].wsq, v.zeros, w.D[l], n, c.cout, c.cin, stream)) return r;
         const int64_t cnt2 = n * c.cout;
         sy_rsqrt_eps_kernel<<<(unsigned)((cnt2 + 255) / 256), 256, 0, st>>>(w.D[l], cnt2);
         GSB_CHECK_LAUNCH();
@@ -425,12 +520,30 @@ extern "C" int gsb_synthesis_forward(const void *d_packed, const gsb_styled_conv
                                                                                 w.act[0][1], v.overflow);
         GSB_CHECK_LAUNCH();
     }
+    const float *rgb_prev = nullptr;
     for (int l = 0; l < n_run; ++l) {
         const gsb_styled_conv &c = layers[l];
         const int src = l & 1, dst = src ^ 1;
         const bool hooked = (l == n_run - 1);
         const int H = c.res_in, ro = res_out_of(c), hw_in = H * H, hw_out = ro * ro;
         const int spc = chunk_samples(c);
+        // ToRGB after conv1 and after the second conv of every resolution (model.py:546-561)
+        const int j = l / 2;
+        const bool with_rgb = (l % 2 == 0) && j < n_rgb;
+        float *rgb_cur = nullptr;
+        if (with_rgb) {
+            const gsb_to_rgb &t = rgbs[j];
+            GSB_CHECK_ARG(t.conv_weight && t.mod_weight && t.mod_bias && t.bias && t.cin == c.cout && (c.cout & (c.cout - 1)) == 0,
+                          "synthesis: ToRGB %d does not match layer %d (cin=%d, cout=%d)", j, l, t.cin, c.cout);
+            rgb_cur = (j == n_rgb - 1) ? d_rgb_out : w.rgb[j & 1];
+            const float mscale = (float)(1.0 / sqrt((double)style_dim));
+            sy_scale_copy_kernel<<<64, 256, 0, st>>>(t.mod_weight, (int64_t)c.cout * style_dim, mscale, nullptr, w.rgb_modw);
+            GSB_CHECK_LAUNCH();
+            if (int r = sy_linear(latent(2 * j + 1), w.rgb_modw, t.mod_bias, w.rgb_s, n, c.cout, style_dim, stream)) return r;
+            const int64_t tot = n * hw_out;
+            sy_rgb_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(t.bias, rgb_prev, n, ro, rgb_cur);
+            GSB_CHECK_LAUNCH();
+        }
         for (int64_t b0 = 0; b0 < n; b0 += spc) {
             const int64_t nb = (b0 + spc <= n) ? spc : (n - b0);
             const int64_t rows = nb * hw_in;
@@ -443,9 +556,13 @@ extern "C" int gsb_synthesis_forward(const void *d_packed, const gsb_styled_conv
             e.s_next = hooked ? nullptr : w.S[l + 1] + b0 * c.cout;
             e.out_hi = hooked ? nullptr : w.act[dst][0] + b0 * hw_out * c.cout;
             e.out_lo = hooked ? nullptr : w.act[dst][1] + b0 * hw_out * c.cout;
-            e.out_f32 = hooked ? d_out + b0 * ld_out : nullptr;
+            e.out_f32 = (hooked && d_out) ? d_out + b0 * ld_out : nullptr;
             e.ld = ld_out;
             e.overflow = v.overflow;
+            e.rgb_w = with_rgb ? rgbs[j].conv_weight : nullptr;
+            e.rgb_s = with_rgb ? w.rgb_s + b0 * c.cout : nullptr;
+            e.rgb_out = with_rgb ? rgb_cur + b0 * hw_out * 3 : nullptr;
+            e.rgb_scale = (float)(1.0 / sqrt((double)c.cout));
             const int cq = c.cout / 4;
             if (c.upsample) {
                 const int64_t t_total = nb * (2 * H + 1) * (2 * H + 1) * cq;
@@ -460,8 +577,32 @@ extern "C" int gsb_synthesis_forward(const void *d_packed, const gsb_styled_conv
                 GSB_CHECK_LAUNCH();
             }
         }
+        if (with_rgb) rgb_prev = rgb_cur;
     }
     return GSB_OK;
+}
+
+}  // namespace gsb
+
+extern "C" int gsb_synthesis_forward(const void *d_packed, const gsb_styled_conv *layers, int n_layers, int n_run, int style_dim,
+                                     const float *d_w, int64_t n, float *d_out, int64_t ld_out, void *d_workspace,
+                                     size_t workspace_bytes, gsb_stream_t stream) {
+    GSB_CHECK_ARG(d_out, "synthesis_forward: null output");
+    return gsb::synthesis_run(d_packed, layers, n_layers, n_run, style_dim, nullptr, 0, d_w, 1, n, d_out, ld_out, nullptr, d_workspace,
+                              workspace_bytes, stream);
+}
+
+extern "C" size_t gsb_synthesis_render_workspace_bytes(const gsb_styled_conv *layers, int n_run, int64_t n, int style_dim) {
+    if (!layers || n_run < 1 || n_run > gsb::SY_MAX_LAYERS || n < 1) return 0;
+    return gsb::synth_ws(nullptr, layers, n_run, n, true, style_dim).bytes;
+}
+
+// Render path (Generator.forward, model.py:493-571): per-layer latents + the ToRGB / skip chain.
+extern "C" int gsb_synthesis_render(const void *d_packed, const gsb_styled_conv *layers, int n_layers, int n_run, int style_dim,
+                                    const gsb_to_rgb *rgbs, int n_rgb, const float *d_w, int w_layers, int64_t n, float *d_act_out,
+                                    int64_t ld_act, float *d_rgb_out, void *d_workspace, size_t workspace_bytes, gsb_stream_t stream) {
+    return gsb::synthesis_run(d_packed, layers, n_layers, n_run, style_dim, rgbs, n_rgb, d_w, w_layers, n, d_act_out, ld_act, d_rgb_out,
+                              d_workspace, workspace_bytes, stream);
 }
 
 extern "C" int gsb_synthesis_status(const void *d_packed, const gsb_styled_conv *layers, int n_layers, int style_dim, unsigned *h_flags) {

@@ -15,6 +15,7 @@ synthesis are not on the path and raise.
 from __future__ import annotations
 
 import math
+import random
 
 import torch
 from torch import nn
@@ -189,13 +190,26 @@ class StyledConv(nn.Module):
                     upsample=c.upsample, res_in=res_in)
 
 
-class ToRGB(_NotBuilt):
+class ToRGB(nn.Module):
+    """model.py:344-363.  The arithmetic (1x1 modulated conv without demodulation, bias, up-sampled skip) is fused into the
+    epilogue of the StyledConv it follows (gsb_synthesis_render); ``forward(_result=skip)`` hands the result to the hooks."""
+
     def __init__(self, in_channel, style_dim, upsample=True, blur_kernel=(1, 3, 3, 1)):
         super().__init__()
         if upsample:
             self.upsample = Upsample(blur_kernel)
         self.conv = ModulatedConv2d(in_channel, 3, 1, style_dim, demodulate=False)
         self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
+
+    def forward(self, input=None, style=None, skip=None, _result=None):
+        if _result is None:
+            raise NotImplementedError("ToRGB runs inside the fused synthesis chain (Generator.forward / partial_forward)")
+        return _result
+
+    def describe(self):
+        c = self.conv
+        return dict(conv_weight=c.weight[0, :, :, 0, 0], mod_weight=c.modulation.weight, mod_bias=c.modulation.bias,
+                    bias=self.bias.reshape(3))
 
 
 class NamedTensor(nn.Module):
@@ -245,6 +259,36 @@ class Generator(nn.Module):
     def get_latent(self, z):
         return self.style(z)
 
-    def forward(self, styles, **kwargs):
-        raise NotImplementedError(
-            "Generator.forward (full synthesis to RGB) is SURVEY.md section 8(f) item 2; not built in this round")
+    def latents_per_layer(self, styles, inject_index=None):
+        """model.py:527-552: the [N, n_latent, style_dim] latent of a forward call from one, two or n_latent styles."""
+        if len(styles) == 1:
+            if styles[0].ndim < 3:
+                return styles[0].unsqueeze(1).repeat(1, self.n_latent, 1)
+            return styles[0]
+        if len(styles) == 2:
+            if inject_index is None:
+                inject_index = random.randint(1, self.n_latent - 1)
+            latent = styles[0].unsqueeze(1).repeat(1, inject_index, 1)
+            latent2 = styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)
+            return self.strided_style(torch.cat([latent, latent2], 1))
+        assert len(styles) == self.n_latent, f"Expected {self.n_latent} latents, got {len(styles)}"
+        return self.strided_style(torch.stack(styles, dim=1))
+
+    def forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None, input_is_w=False,
+                noise=None, randomize_noise=True, _synthesis=None):
+        """model.py:493-571 on the fused chain (``_synthesis``: the wrapper's PackedSynthesis over all StyledConv layers, which
+        holds the fixed noise maps -- the reference wrapper always passes them, wrappers.py:188-192)."""
+        if _synthesis is None:
+            raise NotImplementedError("Generator.forward needs the wrapper's packed synthesis chain (StyleGAN2.forward); "
+                                      "randomised noise is not built")
+        if not input_is_w:
+            styles = [self.style(s) for s in styles]
+        if truncation < 1:
+            styles = [truncation_latent + truncation * (s - truncation_latent) for s in styles]
+        latent = self.latents_per_layer(styles, inject_index)                       # [N, n_latent, S]
+        mods = [self.conv1] + list(self.convs)
+        rgbs = [self.to_rgb1] + list(self.to_rgbs)
+        w_layers = latent.permute(1, 0, 2).contiguous()
+        _, img = _synthesis.render(w_layers, len(mods), [r.describe() for r in rgbs])
+        image = img.permute(0, 3, 1, 2)                                            # NCHW view of the NHWC skip image
+        return (image, latent) if return_latents else (image, None)

@@ -260,10 +260,39 @@ class StyleGAN2(BaseModel):
             raise RuntimeError("StyleGAN2: cannot change output class without reloading")
 
     def forward(self, x):
+        """wrappers.py:188-192: images in [0, 1] (before clamping) from one latent, a pair, or one latent per layer.  Hooked
+        StyledConv / ToRGB layers receive their activations (retain_layer works); an edit installed on a hooked layer would
+        have to be re-fed into the fused chain, which is not built -- it raises instead of being silently ignored."""
         x = x if isinstance(x, list) else [x]
-        out, _ = self.model(x, noise=self.noise, truncation=self.truncation,
-                            truncation_latent=self.latent_avg, input_is_w=self.w_primary)
+        names = self.synthesis_layer_names()
+        syn = self._synthesis(len(names))
+        out, latent = self.model(x, noise=self.noise, truncation=self.truncation, truncation_latent=self.latent_avg,
+                                 input_is_w=self.w_primary, return_latents=True, _synthesis=syn)
+        self._fire_hooks(latent, len(names) - 1, rgb_upto=len(self.model.to_rgbs))
         return 0.5 * (out + 1)
+
+    def _fire_hooks(self, latent, target, rgb_upto=-1):
+        """Hand the activations of hooked StyledConv layers 0..target (and hooked ToRGB layers 0..rgb_upto) to their hooks:
+        each gets its own run of the fused chain up to that layer."""
+        mods = [self.model.conv1] + list(self.model.convs)
+        rgbs = [self.model.to_rgb1] + list(self.model.to_rgbs)
+        w_layers = latent.permute(1, 0, 2).contiguous()
+        for i in range(target + 1):
+            if len(mods[i]._forward_hooks):
+                syn = self._synthesis(i + 1)
+                res, co = syn.shapes[i]
+                act, _ = syn.render(w_layers, i + 1, [], want_act=True)
+                act = act.view(-1, res, res, co).permute(0, 3, 1, 2)                   # NCHW view of NHWC storage
+                if mods[i](_result=act) is not act:
+                    raise NotImplementedError(f"an edit on layer '{self.synthesis_layer_names()[i]}' cannot be propagated through "
+                                              "the fused synthesis chain")
+        for j in range(rgb_upto + 1):
+            if len(rgbs[j]._forward_hooks):
+                syn = self._synthesis(2 * j + 1)
+                _, img = syn.render(w_layers, 2 * j + 1, [r.describe() for r in rgbs[:j + 1]])
+                img = img.permute(0, 3, 1, 2)
+                if rgbs[j](_result=img) is not img:
+                    raise NotImplementedError("an edit on a ToRGB layer cannot be propagated through the fused synthesis chain")
 
     # ---- synthesis chain conv1, convs.0 .. convs.k (wrappers.py:224-255) ------------------------------------
     def synthesis_layer_names(self):
@@ -306,31 +335,30 @@ class StyleGAN2(BaseModel):
         return self._synthesis(n_run).forward(w.reshape(-1, 512), n_run, out=out)
 
     def partial_forward(self, x, layer_name):
+        """wrappers.py:194-259: run up to (and including) the named layer; side effect = its hooks fire.  ``x``: one latent, a
+        pair (style mixing at a random index, as the reference) or one latent per layer."""
         styles = x if isinstance(x, list) else [x]
         if not self.w_primary:
             styles = [self.model.style(s) for s in styles]
         if "style" in layer_name:
+            # (the reference builds the [N, n_latent, 512] repeat + StridedStyle stack before this early exit, wrappers.py:202-222 --
+            # 328 MB of traffic per 10k batch that nothing reads; skipped here)
             return
+        latent = self.model.latents_per_layer(styles)             # [N, n_latent, 512]
         if layer_name == "input":
-            self.model.input(styles[0])
+            self.model.input(latent[:, 0])
             return
         names = self.synthesis_layer_names()
-        if layer_name not in names:
-            raise NotImplementedError(
-                f"StyleGAN2.partial_forward to layer '{layer_name}': only style, input, conv1 and convs.k are on the "
-                "B200 hot path (ToRGB / image synthesis: SURVEY.md section 8f); there is no PyTorch fallback")
-        if len(styles) != 1:
-            raise NotImplementedError("style mixing (several latents per sample) is not built for the fused synthesis chain")
-        mods = [self.model.conv1] + list(self.model.convs)
-        target = names.index(layer_name)
-        w = styles[0].reshape(-1, 512)
-        # the chain runs fused; layers before the target that carry hooks get their own (shorter) run
-        hooked = [i for i in range(target) if len(mods[i]._forward_hooks)]
-        for i in hooked + [target]:
-            syn = self._synthesis(target + 1)
-            res, co = syn.shapes[i]
-            act = syn.forward(w, i + 1).view(-1, res, res, co).permute(0, 3, 1, 2)    # NCHW view of NHWC storage
-            mods[i](_result=act)
+        rgb_names = ["to_rgb1"] + [f"to_rgbs.{i}" for i in range(len(self.model.to_rgbs))]
+        if layer_name in names:
+            target = names.index(layer_name)
+            # the reference computes every to_rgb that precedes the target as well (wrappers.py:232-255)
+            self._fire_hooks(latent, target, rgb_upto=(target - 1) // 2 if target >= 1 else -1)
+        elif layer_name in rgb_names:
+            j = rgb_names.index(layer_name)
+            self._fire_hooks(latent, 2 * j, rgb_upto=j)
+        else:
+            raise RuntimeError(f"Unknown layer '{layer_name}'")
 
     def set_noise_seed(self, seed):
         # same generator stream as the reference (torch.manual_seed(seed); torch.randn per noise map),

@@ -56,5 +56,52 @@ def main():
         np.savez_compressed(OUT / "c5_stylegan2_ffhq_convs4_z_n4000_b500_c4.npz", dump_name=np.array(name), **out)
 
 
+def deep_synthesis_golden():
+    """G11 (`python oracle/gen_golden_r2.py g11`): the layers after convs.4 and the full forward, from the unmodified reference.
+    Perturbed noise weights / activation biases on EVERY StyledConv and non-zero ToRGB biases (all zero at random init).
+      * partial_forward known answers at convs.5 .. convs.15 (strided subsample + sum / sum of squares), one latent
+      * to_rgb1 / to_rgbs.k outputs (the running skip image) at every resolution, same latent
+      * StyleGAN2.forward(z) for two latents (1024^2, stored ::4) and forward(list of 18 per-layer latents) (style mixing)"""
+    ref = rh.import_reference()
+    dev = torch.device("cpu")
+    m = rh.rand_init_stylegan2(ref, dev, "ffhq", 1234)
+    conv_names = ["conv1"] + [f"convs.{i}" for i in range(16)]
+    perturb_synthesis(m.model, conv_names)
+    rgb_names = ["to_rgb1"] + [f"to_rgbs.{i}" for i in range(8)]
+    mods = dict(m.model.named_modules())
+    with torch.no_grad():
+        for i, nme in enumerate(rgb_names):
+            mods[nme].bias.copy_(0.05 * torch.tensor([1.0, -2.0, 3.0]).view(1, 3, 1, 1) * (i + 1))
+    m.use_z()
+    z = m.sample_latent(2, seed=21)
+    ka = dict(z=z.numpy(), rgb_names=np.array(rgb_names), conv_names=np.array(conv_names))
+    for layer in [f"convs.{i}" for i in range(5, 16)] + rgb_names:
+        inst = ref.wrappers.get_instrumented_model("StyleGAN2", "ffhq", layer, dev, model=m, use_w=False)
+        with torch.no_grad():
+            m.partial_forward(z[:1], layer)
+        act = inst.retained_features()[layer].numpy()
+        key = layer.replace(".", "_")
+        step = max(1, act.shape[-1] // 32)
+        ka[f"act_{key}_sub"] = act[:, ::max(1, act.shape[1] // 16), ::step, ::step].copy()
+        ka[f"sum_{key}"] = np.array([act.astype(np.float64).sum(), (act.astype(np.float64) ** 2).sum()])
+        ka[f"shape_{key}"] = np.array(act.shape)
+        inst.close()
+    with torch.no_grad():
+        img = m.forward(z).numpy()                                   # [2, 3, 1024, 1024] in [0, 1]-ish (0.5 * (out + 1))
+        n_lat = m.get_max_latents()
+        mixed = m.forward([z[:1]] * 8 + [z[1:2]] * (n_lat - 8)).numpy()
+        same = m.forward([z[:1]] * n_lat).numpy()
+    assert np.abs(same - img[:1]).max() < 1e-4
+    ka["img_sub"] = img[:, :, ::4, ::4].copy()
+    ka["img_sum"] = np.array([img.astype(np.float64).sum(), (img.astype(np.float64) ** 2).sum()])
+    ka["mixed_sub"] = mixed[:, :, ::4, ::4].copy()
+    ka["mixed_sum"] = np.array([mixed.astype(np.float64).sum(), (mixed.astype(np.float64) ** 2).sum()])
+    np.savez_compressed(OUT / "synthesis_deep_known_answers.npz", **ka)
+    print("wrote synthesis_deep_known_answers.npz", {k: v.shape for k, v in ka.items() if k.endswith("_sub")})
+
+
 if __name__ == "__main__":
-    main()
+    if "g11" in sys.argv[1:]:
+        deep_synthesis_golden()
+    if not sys.argv[1:] or {"g9", "g10"} & set(sys.argv[1:]):
+        main()
