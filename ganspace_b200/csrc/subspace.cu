@@ -43,6 +43,7 @@ struct SubspaceParams {
     double *Prof;                                // [16] clocks per phase, accumulated by CTA 0 (profiling aid)
     int d, c;
     double n_seen, n_b, tol;                     // n_seen < 0: read it from hdr[0] (persistent kernel)
+    double dbl;                                  // residual > dbl * tol: two multiplications by G per orthonormalisation
     int maxit;
     int *status;
 };
@@ -307,103 +308,109 @@ __device__ __forceinline__ void subspace_step_body(const SubspaceParams &p) {
     double rel = 0.0;
     int it = 0;
     bool conv = false;
-    for (;; ++it) {
-        // ---- Y_q = G_q Q   (K = d streamed in stages of SC_KT)
+    // Y_q (or Z_q) = G_q B  -> Ys   (K = d streamed in stages of SC_KT; B = the current Q, or the published Y of a double step)
+    auto gemm_into_ys = [&](const double *Bsrc) {
         {
-            double acc[SC_MAXG][SC_NB][2];
+        double acc[SC_MAXG][SC_NB][2];
 #pragma unroll
-            for (int q = 0; q < SC_MAXG; ++q) zero_acc(acc[q]);
-            for (int s = 0; s < SC_STAGES - 1; ++s) {
-                if (s < nkt) {
-                    cta_copy_async(As + (size_t)s * tileA, Gmine + (size_t)s * tileA, (int)tileA);
-                    cta_copy_async(Bs + (size_t)s * tileB, Qc + (size_t)s * tileB, (int)tileB);
+        for (int q = 0; q < SC_MAXG; ++q) zero_acc(acc[q]);
+        for (int s = 0; s < SC_STAGES - 1; ++s) {
+            if (s < nkt) {
+                cta_copy_async(As + (size_t)s * tileA, Gmine + (size_t)s * tileA, (int)tileA);
+                cta_copy_async(Bs + (size_t)s * tileB, Bsrc + (size_t)s * tileB, (int)tileB);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int kt = 0; kt < nkt; ++kt) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(SC_STAGES - 2) : "memory");
+            __syncthreads();
+            {
+                const int nx = kt + SC_STAGES - 1;
+                if (nx < nkt) {
+                    cta_copy_async(As + (size_t)(nx % SC_STAGES) * tileA, Gmine + (size_t)nx * tileA, (int)tileA);
+                    cta_copy_async(Bs + (size_t)(nx % SC_STAGES) * tileB, Bsrc + (size_t)nx * tileB, (int)tileB);
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
-            for (int kt = 0; kt < nkt; ++kt) {
-                asm volatile("cp.async.wait_group %0;" ::"n"(SC_STAGES - 2) : "memory");
-                __syncthreads();
-                {
-                    const int nx = kt + SC_STAGES - 1;
-                    if (nx < nkt) {
-                        cta_copy_async(As + (size_t)(nx % SC_STAGES) * tileA, Gmine + (size_t)nx * tileA, (int)tileA);
-                        cta_copy_async(Bs + (size_t)(nx % SC_STAGES) * tileB, Qc + (size_t)nx * tileB, (int)tileB);
-                    }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                }
-                const double *At = As + (size_t)(kt % SC_STAGES) * tileA, *Bt = Bs + (size_t)(kt % SC_STAGES) * tileB;
-#pragma unroll
-                for (int q = 0; q < SC_MAXG; ++q) {
-                    const int g = warp + q * SC_WARPS;
-                    if (g < gy.ngroups) {
-                        const int rt = g % gy.mt, ct0 = (g / gy.mt) * gy.nbsel;
-                        const int nb = (gy.nt - ct0 < gy.nbsel) ? gy.nt - ct0 : gy.nbsel;
-                        mma_group<false, false>(At, SC_LDA, Bt, cp, SC_KT / 4, rt * 8, ct0 * 8, nb, acc[q]);
-                    }
-                }
-            }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const double *At = As + (size_t)(kt % SC_STAGES) * tileA, *Bt = Bs + (size_t)(kt % SC_STAGES) * tileB;
 #pragma unroll
             for (int q = 0; q < SC_MAXG; ++q) {
                 const int g = warp + q * SC_WARPS;
                 if (g < gy.ngroups) {
                     const int rt = g % gy.mt, ct0 = (g / gy.mt) * gy.nbsel;
                     const int nb = (gy.nt - ct0 < gy.nbsel) ? gy.nt - ct0 : gy.nbsel;
-#pragma unroll
-                    for (int b = 0; b < SC_NB; ++b)
-                        if (b < nb) {
-                            double *o = Ys + (size_t)(rt * 8 + fg) * cp + (ct0 + b) * 8 + 2 * ft;
-                            o[0] = acc[q][b][0]; o[1] = acc[q][b][1];
-                        }
+                    mma_group<false, false>(At, SC_LDA, Bt, cp, SC_KT / 4, rt * 8, ct0 * 8, nb, acc[q]);
                 }
             }
         }
-        __syncthreads();
-        PROF(2);
-        // ---- partial H~ = Q_q^T Y_q and W = Y_q^T Y_q  -> L2
-        {
-            double *Ph = p.Part + (size_t)me * E, *Pw = Ph + (size_t)c * c;
-            for (int g = warp; g < gh.ngroups; g += SC_WARPS) {
-                const int mt = g % gh.mt, ct0 = (g / gh.mt) * gh.nbsel;
-                const int nb = (gh.nt - ct0 < gh.nbsel) ? gh.nt - ct0 : gh.nbsel;
-                double ah[SC_NB][2], aw[SC_NB][2];
-                zero_acc(ah); zero_acc(aw);
-                mma_group<true, false>(Qq, cp, Ys, cp, RPC / 4, mt * 8, ct0 * 8, nb, ah);
-                mma_group<true, false>(Ys, cp, Ys, cp, RPC / 4, mt * 8, ct0 * 8, nb, aw);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < SC_MAXG; ++q) {
+            const int g = warp + q * SC_WARPS;
+            if (g < gy.ngroups) {
+                const int rt = g % gy.mt, ct0 = (g / gy.mt) * gy.nbsel;
+                const int nb = (gy.nt - ct0 < gy.nbsel) ? gy.nt - ct0 : gy.nbsel;
 #pragma unroll
                 for (int b = 0; b < SC_NB; ++b)
                     if (b < nb) {
-                        const size_t o = (size_t)(mt * 8 + fg) * c + (ct0 + b) * 8 + 2 * ft;
-                        *reinterpret_cast<double2 *>(Ph + o) = make_double2(ah[b][0], ah[b][1]);
-                        *reinterpret_cast<double2 *>(Pw + o) = make_double2(aw[b][0], aw[b][1]);
+                        double *o = Ys + (size_t)(rt * 8 + fg) * cp + (ct0 + b) * 8 + 2 * ft;
+                        o[0] = acc[q][b][0]; o[1] = acc[q][b][1];
                     }
             }
         }
-        __syncthreads();
-        PROF(3);
-        sc_cluster_sync();                                   // (1) all partials are in L2
-        for (int q0 = 0; q0 < slice; q0 += 4 * SC_THREADS) {                  // 64 loads in flight per thread
-            double v[4][SC_CL];
+    }
+    };
+    // partial H~ = Q_q^T Ys and W = Ys^T Ys -> L2, reduced over the cluster into p.Red (two cluster barriers)
+    auto partial_reduce = [&]() {
+    // ---- partial H~ = Q_q^T Y_q and W = Y_q^T Y_q  -> L2
+    {
+        double *Ph = p.Part + (size_t)me * E, *Pw = Ph + (size_t)c * c;
+        for (int g = warp; g < gh.ngroups; g += SC_WARPS) {
+            const int mt = g % gh.mt, ct0 = (g / gh.mt) * gh.nbsel;
+            const int nb = (gh.nt - ct0 < gh.nbsel) ? gh.nt - ct0 : gh.nbsel;
+            double ah[SC_NB][2], aw[SC_NB][2];
+            zero_acc(ah); zero_acc(aw);
+            mma_group<true, false>(Qq, cp, Ys, cp, RPC / 4, mt * 8, ct0 * 8, nb, ah);
+            mma_group<true, false>(Ys, cp, Ys, cp, RPC / 4, mt * 8, ct0 * 8, nb, aw);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int el = me * slice + q0 + u * SC_THREADS + tid;
-                const bool ok = (q0 + u * SC_THREADS + tid < slice) && el < E;
-#pragma unroll
-                for (int r = 0; r < SC_CL; ++r) v[u][r] = ok ? __ldcg(p.Part + (size_t)r * E + el) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int el = me * slice + q0 + u * SC_THREADS + tid;
-                if ((q0 + u * SC_THREADS + tid < slice) && el < E) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int r = 0; r < SC_CL; ++r) s += v[u][r];                       // fixed order: deterministic
-                    p.Red[el] = s;
+            for (int b = 0; b < SC_NB; ++b)
+                if (b < nb) {
+                    const size_t o = (size_t)(mt * 8 + fg) * c + (ct0 + b) * 8 + 2 * ft;
+                    *reinterpret_cast<double2 *>(Ph + o) = make_double2(ah[b][0], ah[b][1]);
+                    *reinterpret_cast<double2 *>(Pw + o) = make_double2(aw[b][0], aw[b][1]);
                 }
+        }
+    }
+    __syncthreads();
+    sc_cluster_sync();                                   // (1) all partials are in L2
+    for (int q0 = 0; q0 < slice; q0 += 4 * SC_THREADS) {                  // 64 loads in flight per thread
+        double v[4][SC_CL];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int el = me * slice + q0 + u * SC_THREADS + tid;
+            const bool ok = (q0 + u * SC_THREADS + tid < slice) && el < E;
+#pragma unroll
+            for (int r = 0; r < SC_CL; ++r) v[u][r] = ok ? __ldcg(p.Part + (size_t)r * E + el) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int el = me * slice + q0 + u * SC_THREADS + tid;
+            if ((q0 + u * SC_THREADS + tid < slice) && el < E) {
+                double s = 0.0;
+#pragma unroll
+                for (int r = 0; r < SC_CL; ++r) s += v[u][r];                       // fixed order: deterministic
+                p.Red[el] = s;
             }
         }
+    }
+    __syncthreads();
+    sc_cluster_sync();                                   // (2) reduced H~ and W are in L2
+    };
+    for (;;) {
+        gemm_into_ys(Qc);
         __syncthreads();
-        sc_cluster_sync();                                   // (2) reduced H~ and W are in L2
+        PROF(2);
+        partial_reduce();
         for (int i = tid; i < c * c; i += SC_THREADS) Ws[(i / c) * cp + i % c] = __ldcg(p.Red + i);
         __syncthreads();
         PROF(4);
@@ -443,7 +450,21 @@ __device__ __forceinline__ void subspace_step_body(const SubspaceParams &p) {
         }
         PROF(5);
         if (conv || it >= p.maxit) break;
-        // ---- W = L L^T in shared memory; the rows of Y_q ride along:  Y_q <- Y_q L^-T
+        ++it;
+        if (rel > p.dbl * p.tol && it < p.maxit) {
+            // Far from converged: multiply by G once more before orthonormalising, Z = G Y (two iterations of convergence for
+            // one Cholesky; cond(Z) <= (lambda_1 / lambda_c)^2, harmless in fp64).  Y becomes the B operand: publish it.
+            double *dst = Qn + (size_t)me * RPC * cp;
+            for (int i = tid; i < RPC * cp; i += SC_THREADS) dst[i] = ((i % cp) < c) ? Ys[i] : 0.0;
+            __syncthreads();
+            sc_cluster_sync();                               // Y is complete in L2
+            gemm_into_ys(Qn);
+            __syncthreads();
+            partial_reduce();                                // only W = Z^T Z is used
+            ++it;
+            PROF(2);
+        }
+        // ---- W = L L^T in shared memory; the rows of Y_q (Z_q) ride along:  Q_q <- Y_q L^-T
         for (int i = tid; i < c * c; i += SC_THREADS) Ws[(i / c) * cp + i % c] = __ldcg(p.Red + (size_t)c * c + i);
         __syncthreads();
         chol_solve_regs<RA, CB>(Ws, Ys, c, cp, RPC, colbuf);
@@ -659,6 +680,19 @@ SubspaceWs carve_subspace(void *base, int d, int c) {
     return w;
 }
 
+// residual / tolerance ratio above which an iteration multiplies by G twice before orthonormalising (GANSPACE_B200_SUBSPACE_DBL;
+// 0 = never).  One multiplication gains a factor lambda_{c+1}/lambda_c ~ 1/k at step k, so "more than 10x away" means at least
+// two more iterations early in a run and costs at most one spare GEMM late in it.
+static double double_step_factor() {
+    static double f = -1.0;
+    if (f < 0.0) {
+        const char *e = getenv("GANSPACE_B200_SUBSPACE_DBL");
+        f = e ? atof(e) : 10.0;
+        if (!(f > 0.0)) f = 1e300;
+    }
+    return f;
+}
+
 int subspace_step(double *hdr, double *mean, double *unnorm, double *H, double *Qbuf, const double *mean_b, const double *gram_b,
                   const SubspaceWs &w, int d, int c, double n_seen, double n_b, cudaStream_t st) {
     static double tol = -1.0;
@@ -689,7 +723,7 @@ int subspace_step(double *hdr, double *mean, double *unnorm, double *H, double *
     p.hdr = hdr; p.mean = mean; p.unnorm = unnorm; p.H = H; p.Qbuf = Qbuf;
     p.mean_b = mean_b; p.gram_b = gram_b;
     p.Gt = w.Gt; p.Part = w.Part; p.Red = w.Red; p.Slots = w.Slots; p.Prof = hdr + 8;
-    p.d = d; p.c = c; p.n_seen = n_seen; p.n_b = n_b; p.tol = tol; p.maxit = maxit;
+    p.d = d; p.c = c; p.n_seen = n_seen; p.n_b = n_b; p.tol = tol; p.maxit = maxit; p.dbl = double_step_factor();
     p.status = eig_status_device_ptr();
     GSB_CHECK_ARG(p.status, "subspace_step: no device status word");
     cudaLaunchConfig_t cfg{};
@@ -751,7 +785,7 @@ int subspace_run_persistent(double *hdr, double *mean, double *unnorm, double *H
     p.hdr = hdr; p.mean = mean; p.unnorm = unnorm; p.H = H; p.Qbuf = Qbuf;
     p.mean_b = nullptr; p.gram_b = nullptr;
     p.Gt = w.Gt; p.Part = w.Part; p.Red = w.Red; p.Slots = w.Slots; p.Prof = hdr + 8;
-    p.d = d; p.c = c; p.n_seen = -1.0; p.n_b = n_b; p.tol = tol; p.maxit = maxit;
+    p.d = d; p.c = c; p.n_seen = -1.0; p.n_b = n_b; p.tol = tol; p.maxit = maxit; p.dbl = double_step_factor();
     p.status = eig_status_device_ptr();
     GSB_CHECK_ARG(p.status, "subspace_run_persistent: no device status word");
     ChainQueueEntry *q = reinterpret_cast<ChainQueueEntry *>(queue);
