@@ -337,6 +337,28 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
 
+    # ---- the roofline kernel alone (outside the timed region): same rows, nothing else on the GPU -------------------------
+    isolated = None
+    if w["section"] == "mapping" and rank == 0:
+        rows_iso = int(rows.get("mapping", 0) // max(1, args.steps)) or w["n"]
+        packed = model.model.style.packed()
+        zi = torch.randn((rows_iso, 512), device=dev, dtype=torch.float32)
+        oi = torch.empty_like(zi)
+        for _ in range(2):
+            packed.forward(zi, out=oi)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); packed.forward(zi, out=oi); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        iso_ms = sorted(ts)[1]
+        isolated = {"rows": rows_iso, "ms": iso_ms, "achieved": rows_iso * w["flop"] / (iso_ms * 1e-3) / 1e12}
+        del zi, oi
+    if world > 1:
+        dist.barrier()
+
     # ---- parity (outside the timed region): properties of the full-size result; a small-N run vs the oracle ---------
     parity = None
     if rank == 0:
@@ -392,7 +414,10 @@ def run_ours(args):
                                  "value x FLOP/sample / (peak x n_gpus), SURVEY.md section 8d",
                          "peak_source": f"bf16_tflops_sustained, {peak_kind} (MEASURED_PEAKS.json)",
                          "ms_per_step": sec_ms_step, "launches_per_step": sec_calls / max(1, args.steps),
-                         "rows_per_step": sec_rows / max(1, args.steps)},
+                         "rows_per_step": sec_rows / max(1, args.steps),
+                         "isolated": (dict(isolated, frac=isolated["achieved"] / peak, frac_of_burst_peak=isolated["achieved"] / peaks["bf16_tflops"],
+                                           note="the same kernel on the same number of rows with nothing else running, measured "
+                                                "after the timed region (median of 3)") if isolated else None)},
             "sections_ms_per_step": {k: v[0] / args.steps for k, v in sections.items()},
             "parity": parity,
             "clocks": clocks,

@@ -563,13 +563,15 @@ static int tc_ensure_attr() {
     return GSB_OK;
 }
 
-// cluster size of the layer kernel: GANSPACE_B200_MAPPING_CLUSTER = 1 | 2 | 4 (default 4)
+// cluster size of the layer kernel: GANSPACE_B200_MAPPING_CLUSTER = 1 | 2 | 4.  Default 1: weight multicast measured no gain
+// (11.5 ms without, 12.2 ms with 4-CTA clusters for 1.01M rows x 8 layers -- the kernel is bound by shared-memory bandwidth,
+// which multicast does not relieve: every CTA still receives the whole weight tile).
 static int tc_cluster_size() {
     static int cs = 0;
     if (!cs) {
         const char *e = getenv("GANSPACE_B200_MAPPING_CLUSTER");
-        cs = e ? atoi(e) : 4;
-        if (cs != 1 && cs != 2 && cs != 4) cs = 4;
+        cs = e ? atoi(e) : 1;
+        if (cs != 1 && cs != 2 && cs != 4) cs = 1;
     }
     return cs;
 }
@@ -638,9 +640,7 @@ int tc_gemm_plain(const __half *a_hi, const __half *a_lo, int64_t M, int K, cons
     GSB_CHECK_ARG(N % 32 == 0 && N >= 32 && K % 8 == 0 && K >= 8 && M > 0 && M < (1ll << 31),
                   "tc_gemm_plain: need N%%32==0, K%%8==0 (M=%lld N=%d K=%d)", (long long)M, N, K);
     if (int r = tc_ensure_attr()) return r;
-    // few row tiles (a chunk of a conv layer): no cluster, one output tile per work unit; many: weight multicast
-    const int m_tiles = (int)((M + TC_BLOCK_M - 1) / TC_BLOCK_M);
-    const int cs = (m_tiles >= 4 * num_sms()) ? tc_cluster_size() : 1;
+    const int cs = 1;                  // (no weight multicast for the tap GEMMs: see tc_cluster_size)
     CUtensorMap tm_ah, tm_al, tm_wh, tm_wl;
     if (int r = make_tmap_f16(&tm_ah, a_hi, (uint64_t)M, (uint64_t)K, TC_BLOCK_M)) return r;
     if (int r = make_tmap_f16(&tm_al, a_lo, (uint64_t)M, (uint64_t)K, TC_BLOCK_M)) return r;
