@@ -44,6 +44,7 @@ struct SubspaceParams {
     int d, c;
     double n_seen, n_b, tol;                     // n_seen < 0: read it from hdr[0] (persistent kernel)
     double dbl;                                  // residual > dbl * tol: two multiplications by G per orthonormalisation
+    int chol_blocked;                            // 1: panel-of-8 Cholesky (GANSPACE_B200_SUBSPACE_CHOL=blocked|columns)
     int maxit;
     int *status;
 };
@@ -186,6 +187,116 @@ __device__ __forceinline__ void chol_solve_regs(const double *__restrict__ Ws, d
         if (r >= c && r < nrows) {
 #pragma unroll
             for (int b = 0; b < CB; ++b) { const int q = cx + 16 * b; if (q < c) Ys[(size_t)(r - c) * cp + q] = A[a][b]; }
+        }
+    }
+    __syncthreads();
+}
+
+// Blocked form of the above (panels of 8 columns): the per-column barrier + rsqrt + broadcast of the unblocked loop cost 0.59 us per
+// column (47 us for c = 80) although the arithmetic is 0.07 us.  Per panel: (1) the owners publish the panel's 8 columns; (2) warp 0
+// factors the 8 x 8 diagonal block with shuffles (lane l owns row l), then one thread per remaining row solves X = P L^-T (the Y
+// rows of the panel are final here and go straight to Ys); (3) every thread applies the rank-8 update to its registers.
+// Two barriers per panel instead of eight.
+template <int RA, int CB>
+__device__ __forceinline__ void chol_solve_blocked(const double *__restrict__ Ws, double *__restrict__ Ys, int c, int cp, int RPC,
+                                                   double *__restrict__ buf /* [2 * 16 * RA * 9 + 80] */) {
+    const int tid = threadIdx.x, ry = tid >> 4, cx = tid & 15, lane = tid & 31;
+    const int nrows = c + RPC, CL = 16 * RA;
+    double *P = buf, *XS = buf + (size_t)CL * 9, *Lb = XS + (size_t)CL * 9;        // Lb: [8][9] factor, [72..79] inverse diagonal
+    double A[RA][CB];
+#pragma unroll
+    for (int a = 0; a < RA; ++a) {
+        const int r = ry + 16 * a;
+#pragma unroll
+        for (int b = 0; b < CB; ++b) {
+            const int q = cx + 16 * b;
+            double v = 0.0;
+            if (r < nrows && q < c) v = (r < c) ? Ws[(size_t)r * cp + q] : Ys[(size_t)(r - c) * cp + q];
+            A[a][b] = v;
+        }
+    }
+    const double floor_ = fmax(fabs(Ws[0]) * 1e-26, 1e-300);
+    __syncthreads();
+    for (int p = 0; p < c / 8; ++p) {
+        const int j0 = 8 * p, pb = p >> 1, pc = (p & 1) * 8;
+        // (1) panel columns -> P[row][k]
+        if (cx >= pc && cx < pc + 8) {
+#pragma unroll
+            for (int b = 0; b < CB; ++b)
+                if (b == pb) {
+#pragma unroll
+                    for (int a = 0; a < RA; ++a) P[(size_t)(ry + 16 * a) * 9 + (cx - pc)] = A[a][b];
+                }
+        }
+        __syncthreads();
+        // (2a) 8 x 8 Cholesky of the diagonal block in warp 0: lane l (< 8) owns row l
+        if (tid < 32) {
+            const int l = lane & 7;
+            double row[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) row[k] = P[(size_t)(j0 + l) * 9 + k];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                double piv = __shfl_sync(0xffffffffu, row[j], j);
+                if (!(piv > floor_)) piv = floor_;
+                const double inv = fast_rsqrt(piv);
+                const double lij = row[j] * inv;                       // L[l][j] for l >= j
+#pragma unroll
+                for (int k = j + 1; k < 8; ++k) {
+                    const double lkj = __shfl_sync(0xffffffffu, lij, k);
+                    row[k] = fma(-lij, lkj, row[k]);
+                }
+                row[j] = lij;
+                if (lane == j) Lb[72 + j] = inv;                       // 1 / L[j][j]
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) Lb[l * 9 + k] = (k <= l) ? row[k] : 0.0;
+            }
+        }
+        __syncthreads();
+        // (2b) X[r][:] = P[r][:] L^-T for the rows below the panel; one thread per row
+        for (int r = j0 + 8 + tid; r < nrows; r += SC_THREADS) {
+            double x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                double sacc = P[(size_t)r * 9 + k];
+#pragma unroll
+                for (int m = 0; m < k; ++m) sacc = fma(-x[m], Lb[k * 9 + m], sacc);
+                x[k] = sacc * Lb[72 + k];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) XS[(size_t)r * 9 + k] = x[k];
+            if (r >= c) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) Ys[(size_t)(r - c) * cp + j0 + k] = x[k];
+            }
+        }
+        __syncthreads();
+        // (3) rank-8 update of the trailing columns (q >= j0 + 8) for the rows below the panel
+        double xr[RA][8];
+#pragma unroll
+        for (int a = 0; a < RA; ++a) {
+            const int r = ry + 16 * a;
+            const bool ok = (r >= j0 + 8) && (r < nrows);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xr[a][k] = ok ? XS[(size_t)r * 9 + k] : 0.0;
+        }
+#pragma unroll
+        for (int b = 0; b < CB; ++b) {
+            const int q = cx + 16 * b;
+            if (q >= j0 + 8 && q < c) {
+                double xq[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) xq[k] = XS[(size_t)q * 9 + k];
+#pragma unroll
+                for (int a = 0; a < RA; ++a) {
+                    double v = A[a][b];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v = fma(-xr[a][k], xq[k], v);
+                    A[a][b] = v;
+                }
+            }
         }
     }
     __syncthreads();
@@ -467,7 +578,8 @@ __device__ __forceinline__ void subspace_step_body(const SubspaceParams &p) {
         // ---- W = L L^T in shared memory; the rows of Y_q (Z_q) ride along:  Q_q <- Y_q L^-T
         for (int i = tid; i < c * c; i += SC_THREADS) Ws[(i / c) * cp + i % c] = __ldcg(p.Red + (size_t)c * c + i);
         __syncthreads();
-        chol_solve_regs<RA, CB>(Ws, Ys, c, cp, RPC, colbuf);
+        if (p.chol_blocked) chol_solve_blocked<RA, CB>(Ws, Ys, c, cp, RPC, colbuf);
+        else chol_solve_regs<RA, CB>(Ws, Ys, c, cp, RPC, colbuf);
         PROF(6);
         // ---- publish the new rows of Q
         {
@@ -662,8 +774,8 @@ bool subspace_applicable(int d, int c) {
 
 size_t subspace_smem_bytes(int d, int c) {
     const int cp = c + 4, RPC = d / SC_CL;
-    return ((size_t)SC_STAGES * RPC * SC_LDA + (size_t)SC_STAGES * SC_KT * cp + 2 * (size_t)RPC * cp + (size_t)c * cp + d + 64 + 2 * 16 * 10) *
-           sizeof(double);
+    return ((size_t)SC_STAGES * RPC * SC_LDA + (size_t)SC_STAGES * SC_KT * cp + 2 * (size_t)RPC * cp + (size_t)c * cp + d + 64 +
+            2 * 16 * 10 * 9 + 80) * sizeof(double);
 }
 
 SubspaceWs carve_subspace(void *base, int d, int c) {
@@ -683,6 +795,15 @@ SubspaceWs carve_subspace(void *base, int d, int c) {
 // residual / tolerance ratio above which an iteration multiplies by G twice before orthonormalising (GANSPACE_B200_SUBSPACE_DBL;
 // 0 = never).  One multiplication gains a factor lambda_{c+1}/lambda_c ~ 1/k at step k, so "more than 10x away" means at least
 // two more iterations early in a run and costs at most one spare GEMM late in it.
+static int chol_blocked_default() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("GANSPACE_B200_SUBSPACE_CHOL");
+        v = (e && strcmp(e, "columns") == 0) ? 0 : 1;
+    }
+    return v;
+}
+
 static double double_step_factor() {
     static double f = -1.0;
     if (f < 0.0) {
@@ -723,7 +844,7 @@ int subspace_step(double *hdr, double *mean, double *unnorm, double *H, double *
     p.hdr = hdr; p.mean = mean; p.unnorm = unnorm; p.H = H; p.Qbuf = Qbuf;
     p.mean_b = mean_b; p.gram_b = gram_b;
     p.Gt = w.Gt; p.Part = w.Part; p.Red = w.Red; p.Slots = w.Slots; p.Prof = hdr + 8;
-    p.d = d; p.c = c; p.n_seen = n_seen; p.n_b = n_b; p.tol = tol; p.maxit = maxit; p.dbl = double_step_factor();
+    p.d = d; p.c = c; p.n_seen = n_seen; p.n_b = n_b; p.tol = tol; p.maxit = maxit; p.dbl = double_step_factor(); p.chol_blocked = chol_blocked_default();
     p.status = eig_status_device_ptr();
     GSB_CHECK_ARG(p.status, "subspace_step: no device status word");
     cudaLaunchConfig_t cfg{};
@@ -785,7 +906,7 @@ int subspace_run_persistent(double *hdr, double *mean, double *unnorm, double *H
     p.hdr = hdr; p.mean = mean; p.unnorm = unnorm; p.H = H; p.Qbuf = Qbuf;
     p.mean_b = nullptr; p.gram_b = nullptr;
     p.Gt = w.Gt; p.Part = w.Part; p.Red = w.Red; p.Slots = w.Slots; p.Prof = hdr + 8;
-    p.d = d; p.c = c; p.n_seen = -1.0; p.n_b = n_b; p.tol = tol; p.maxit = maxit; p.dbl = double_step_factor();
+    p.d = d; p.c = c; p.n_seen = -1.0; p.n_b = n_b; p.tol = tol; p.maxit = maxit; p.dbl = double_step_factor(); p.chol_blocked = chol_blocked_default();
     p.status = eig_status_device_ptr();
     GSB_CHECK_ARG(p.status, "subspace_run_persistent: no device status word");
     ChainQueueEntry *q = reinterpret_cast<ChainQueueEntry *>(queue);
