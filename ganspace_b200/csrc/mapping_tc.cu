@@ -92,6 +92,25 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+__device__ __forceinline__ void tc_commit2_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -165,6 +184,7 @@ struct TcParams {
     int M, N_total, K;
     int mode;               // 0: (acc 2^-s + bias) -> leaky-ReLU * sqrt2 (EqualLinear);  1: plain acc 2^-s (tc_gemm_plain);  2: acc 2^-s + bias
     int n_groups;           // work units per cluster tile (1 or N_total / 256)
+    int pair;               // 1: CTA pairs (cta_group::2): one 256 x 256 MMA tile per pair, each CTA holds half of the weight tile
     int dbg;                // profiling experiments (GANSPACE_B200_MAPPING_DBG): 1 no stores, 2 no W loads, 4 no A loads, 8 no MMAs
 };
 
@@ -175,10 +195,16 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
                         const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // pair mode (cta_group::2): each CTA stages its own 128 A rows and HALF of the weight tile (128 of the 256 N rows): 64 KB per
+    // stage, three stages; otherwise 96 KB per stage, two stages -- the same 192 KB ring either way
+    const bool pair = p.pair != 0;
+    const int n_stages = pair ? 3 : TC_STAGES;
+    const uint32_t w_tile_bytes = pair ? TC_W_BYTES / 2 : TC_W_BYTES;
+    const uint32_t stage_bytes = 2 * TC_A_BYTES + 2 * w_tile_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint64_t *full_bar = bars;                         // [TC_STAGES]
-    uint64_t *empty_bar = bars + TC_STAGES;            // [TC_STAGES]
-    uint64_t *tfull_bar = bars + 2 * TC_STAGES;        // [TC_ACC_STAGES]
+    uint64_t *full_bar = bars;                         // [3]
+    uint64_t *empty_bar = bars + 3;                    // [3]
+    uint64_t *tfull_bar = bars + 6;                    // [TC_ACC_STAGES]
     uint64_t *tempty_bar = tfull_bar + TC_ACC_STAGES;  // [TC_ACC_STAGES]
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tempty_bar + TC_ACC_STAGES);
 
@@ -200,6 +226,7 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
     const int num_units = num_ct * n_groups;
     const uint16_t mc_mask = (uint16_t)((1u << cs) - 1u);
     const uint32_t w_slice_rows = TC_BLOCK_N / cs, w_slice_bytes = TC_W_BYTES / cs;
+    const bool leader = (crank == 0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
@@ -207,13 +234,20 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
         tma_prefetch_desc(&tm_o0); tma_prefetch_desc(&tm_o1);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], cs); }
-        for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+        // pair mode: the leader's full barrier also takes the peer's "my half has landed" arrival; a stage is released by ONE
+        // commit of the leader (multicast to both CTAs); the leader's accumulator-empty barrier takes both CTAs' epilogue threads
+        for (int s = 0; s < 3; ++s) { mbar_init(&full_bar[s], (pair && leader) ? 2 : 1); mbar_init(&empty_bar[s], pair ? 1 : cs); }
+        for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], pair ? 256 : 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (pair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -232,31 +266,42 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
                     const int n0 = nt * TC_BLOCK_N;
                     for (int kb = 0; kb < num_k_blocks; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);          // the MMAs of every CTA of the cluster have left this stage
-                        uint8_t *st = smem + stage * TC_STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[stage], ((p.dbg & 4) ? 0u : 2 * TC_A_BYTES) + ((p.dbg & 2) ? 0u : 2 * TC_W_BYTES));
+                        uint8_t *st = smem + stage * stage_bytes;
+                        mbar_arrive_expect_tx(&full_bar[stage], ((p.dbg & 4) ? 0u : 2 * TC_A_BYTES) + ((p.dbg & 2) ? 0u : 2 * w_tile_bytes));
                         if (!(p.dbg & 4)) {
                             tma_load_2d(&tm_a_hi, &full_bar[stage], st, kb * TC_BLOCK_K, m0);
                             tma_load_2d(&tm_a_lo, &full_bar[stage], st + TC_A_BYTES, kb * TC_BLOCK_K, m0);
                         }
-                        uint8_t *wh = st + 2 * TC_A_BYTES + crank * w_slice_bytes, *wl = wh + TC_W_BYTES;
-                        const int wrow = n0 + (int)(crank * w_slice_rows);
+                        uint8_t *wh = st + 2 * TC_A_BYTES + (pair ? 0u : crank * w_slice_bytes), *wl = wh + w_tile_bytes;
+                        const int wrow = n0 + (int)(crank * w_slice_rows);          // pair: rows [n0 + crank * 128, + 128)
                         if (p.dbg & 2) {
-                        } else if (cs > 1) {                                      // this CTA's slice of the weight box, to all peers
+                        } else if (cs > 1 && !pair) {                                      // this CTA's slice of the weight box, to all peers
                             tma_load_2d_mc(&tm_w_hi, &full_bar[stage], wh, kb * TC_BLOCK_K, wrow, mc_mask);
                             tma_load_2d_mc(&tm_w_lo, &full_bar[stage], wl, kb * TC_BLOCK_K, wrow, mc_mask);
                         } else {
                             tma_load_2d(&tm_w_hi, &full_bar[stage], wh, kb * TC_BLOCK_K, wrow);
                             tma_load_2d(&tm_w_lo, &full_bar[stage], wl, kb * TC_BLOCK_K, wrow);
                         }
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
+            }
+        }
+    } else if (warp == 1 && pair && !leader) {
+        // ===================== pair mode, peer CTA: tell the leader when this CTA's half of a stage has landed =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const int nkb = ((num_units - cluster_id + num_clusters - 1) / num_clusters) * tiles_per_group * num_k_blocks;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(&full_bar[stage], phase);
+                mbar_arrive_remote(&full_bar[stage], 0);
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(TC_BLOCK_M, TC_BLOCK_N);
+            const uint32_t idesc = pair ? make_idesc_f16(2 * TC_BLOCK_M, TC_BLOCK_N) : make_idesc_f16(TC_BLOCK_M, TC_BLOCK_N);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = 0, ntile = ((num_units - cluster_id + num_clusters - 1) / num_clusters) * tiles_per_group; tile < ntile; ++tile) {
@@ -266,24 +311,32 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);           // TMA bytes have landed
                     tc_fence_after();
-                    const uint32_t st = smem_u32(smem + stage * TC_STAGE_BYTES);
+                    const uint32_t st = smem_u32(smem + stage * stage_bytes);
                     const uint64_t d_ah = make_sw128_kmajor_desc(st);
                     const uint64_t d_al = make_sw128_kmajor_desc(st + TC_A_BYTES);
                     const uint64_t d_wh = make_sw128_kmajor_desc(st + 2 * TC_A_BYTES);
-                    const uint64_t d_wl = make_sw128_kmajor_desc(st + 2 * TC_A_BYTES + TC_W_BYTES);
+                    const uint64_t d_wl = make_sw128_kmajor_desc(st + 2 * TC_A_BYTES + w_tile_bytes);
 #pragma unroll
                     for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
                         if (p.dbg & 8) break;
                         const uint64_t koff = (uint64_t)((k * TC_UMMA_K * 2) >> 4);   // +32 B per K step
-                        tc_mma_f16(tmem_d, d_ah + koff, d_wh + koff, idesc, (kb | k) ? 1u : 0u);
-                        tc_mma_f16(tmem_d, d_al + koff, d_wh + koff, idesc, 1u);
-                        tc_mma_f16(tmem_d, d_ah + koff, d_wl + koff, idesc, 1u);
+                        if (pair) {           // 256 x 256 x 16 over the pair: A rows and B (weight) rows are split between the CTAs
+                            tc_mma2_f16(tmem_d, d_ah + koff, d_wh + koff, idesc, (kb | k) ? 1u : 0u);
+                            tc_mma2_f16(tmem_d, d_al + koff, d_wh + koff, idesc, 1u);
+                            tc_mma2_f16(tmem_d, d_ah + koff, d_wl + koff, idesc, 1u);
+                        } else {
+                            tc_mma_f16(tmem_d, d_ah + koff, d_wh + koff, idesc, (kb | k) ? 1u : 0u);
+                            tc_mma_f16(tmem_d, d_al + koff, d_wh + koff, idesc, 1u);
+                            tc_mma_f16(tmem_d, d_ah + koff, d_wl + koff, idesc, 1u);
+                        }
                     }
-                    if (cs > 1) tc_commit_mc(&empty_bar[stage], mc_mask);   // ... on every CTA of the cluster (their boxes land here too)
+                    if (pair) tc_commit2_mc(&empty_bar[stage], 3);          // both CTAs' stage is free when the pair's MMAs retire
+                    else if (cs > 1) tc_commit_mc(&empty_bar[stage], mc_mask);   // ... on every CTA of the cluster (their boxes land here too)
                     else tc_commit(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull_bar[acc]);                       // accumulator complete -> epilogue
+                if (pair) tc_commit2_mc(&tfull_bar[acc], 3);      // accumulators (one half in each CTA's TMEM) complete -> both epilogues
+                else tc_commit(&tfull_bar[acc]);                  // accumulator complete -> epilogue
                 if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -320,7 +373,8 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
                 tc_wait_ld();
                 if (c0 + 64 == TC_BLOCK_N) {                       // accumulator drained: the MMA warp may refill it
                     tc_fence_before();
-                    mbar_arrive(&tempty_bar[acc]);
+                    if (pair && !leader) mbar_arrive_remote(&tempty_bar[acc], 0);     // the leader issues for both CTAs
+                    else mbar_arrive(&tempty_bar[acc]);
                 }
                 if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging has been read out
                 if (c0 == 0 && p.mode != 1) {                      // (safe: the previous tile's readers passed a barrier below)
@@ -387,7 +441,8 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
     if (cs > 1) cluster_sync_all();                    // no CTA leaves while a peer can still signal its barriers
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -598,7 +653,9 @@ static int tc_max_clusters(int cs) {
 
 // one launch of the layer kernel over `m_tiles` row tiles; W tensor maps must have been built with box rows 256 / cs
 static int tc_launch_layer(const CUtensorMap &tm_ah, const CUtensorMap &tm_al, const CUtensorMap &tm_wh, const CUtensorMap &tm_wl,
-                           TcParams p, int cs, int leave_free_sms, cudaStream_t st) {
+                           TcParams p, int cs, int leave_free_sms, cudaStream_t st, int pair = 0) {
+    p.pair = pair;                       // pair mode needs cs == 2 and W tensor maps with 128-row boxes
+    if (pair && cs != 2) { set_error("tc_launch_layer: pair mode needs clusters of 2"); return GSB_ERR_ARG; }
     // output boxes of the epilogue's TMA stores: fp16 hi / lo [M, N] (the next layer's A operand) or fp32 [M, N]
     CUtensorMap tm_o0, tm_o1;
     if (p.out_f32) {
@@ -707,7 +764,12 @@ int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim,
     // persistent CTAs in clusters, one CTA per SM; `leave_free_sms` keeps some SMs idle for a concurrent latency-critical
     // stream (the IPCA chain's 16-CTA cluster kernels), which otherwise wait for a whole layer launch to drain
     const int m_tiles = (int)((n + TC_BLOCK_M - 1) / TC_BLOCK_M);
-    const int cs = (m_tiles >= 64) ? tc_cluster_size() : 1;
+    // GANSPACE_B200_MAPPING_PAIR=1: CTA pairs issuing tcgen05.mma.cta_group::2 (256 x 256 tiles, each CTA stages half of the
+    // weight tile: 64 B/clk of MMA operand reads and 42 B/clk of TMA fills per SM instead of 96 + 62)
+    static int pair_mode = -1;
+    if (pair_mode < 0) { const char *e = getenv("GANSPACE_B200_MAPPING_PAIR"); pair_mode = (e && atoi(e) == 1) ? 1 : 0; }
+    const int pair = (pair_mode && m_tiles >= 64) ? 1 : 0;
+    const int cs = pair ? 2 : ((m_tiles >= 64) ? tc_cluster_size() : 1);
     const int64_t per = (int64_t)dim * dim;
     for (int l = 0; l < n_layers; ++l) {
         const int src = l & 1, dst = src ^ 1;
@@ -725,7 +787,7 @@ int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim,
         p.overflow = v.overflow;
         p.inv_wscale = v.inv_wscale + l;
         p.M = (int)n; p.N_total = dim; p.K = dim; p.mode = 0; p.n_groups = 1;
-        if (int r = tc_launch_layer(tm_ah, tm_al, tm_wh, tm_wl, p, cs, leave_free_sms, st)) return r;
+        if (int r = tc_launch_layer(tm_ah, tm_al, tm_wh, tm_wl, p, cs, leave_free_sms, st, pair)) return r;
     }
     return GSB_OK;
 }
