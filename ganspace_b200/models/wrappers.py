@@ -350,7 +350,18 @@ class StyleGAN2(BaseModel):
             return
         names = self.synthesis_layer_names()
         rgb_names = ["to_rgb1"] + [f"to_rgbs.{i}" for i in range(len(self.model.to_rgbs))]
-        if layer_name in names:
+        rgb_hooked = any(len(m._forward_hooks) for m in [self.model.to_rgb1] + list(self.model.to_rgbs))
+        if layer_name in names and len(styles) == 1 and not rgb_hooked:
+            # one global latent, no ToRGB hook: the decomposition's own call pattern -- the single-latent entry point
+            mods = [self.model.conv1] + list(self.model.convs)
+            target = names.index(layer_name)
+            w = styles[0].reshape(-1, 512)
+            for i in [i for i in range(target) if len(mods[i]._forward_hooks)] + [target]:
+                syn = self._synthesis(target + 1)
+                res, co = syn.shapes[i]
+                act = syn.forward(w, i + 1).view(-1, res, res, co).permute(0, 3, 1, 2)    # NCHW view of NHWC storage
+                mods[i](_result=act)
+        elif layer_name in names:
             target = names.index(layer_name)
             # the reference computes every to_rgb that precedes the target as well (wrappers.py:232-255)
             self._fire_hooks(latent, target, rgb_upto=(target - 1) // 2 if target >= 1 else -1)
