@@ -188,6 +188,7 @@ struct TcParams {
     int dbg;                // profiling experiments (GANSPACE_B200_MAPPING_DBG): 1 no stores, 2 no W loads, 4 no A loads, 8 no MMAs
 };
 
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                         const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -197,7 +198,9 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     // pair mode (cta_group::2): each CTA stages its own 128 A rows and HALF of the weight tile (128 of the 256 N rows): 64 KB per
     // stage, three stages; otherwise 96 KB per stage, two stages -- the same 192 KB ring either way
-    const bool pair = p.pair != 0;
+    // (PAIR is a template parameter: a kernel that contains cta_group::2 instructions can only be launched with an even cluster
+    // size -- "cluster misconfiguration" otherwise -- so the ordinary instantiation must not contain them)
+    constexpr bool pair = PAIR;
     const int n_stages = pair ? 3 : TC_STAGES;
     const uint32_t w_tile_bytes = pair ? TC_W_BYTES / 2 : TC_W_BYTES;
     const uint32_t stage_bytes = 2 * TC_A_BYTES + 2 * w_tile_bytes;
@@ -241,7 +244,7 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        if (pair) {
+        if constexpr (pair) {
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
         } else {
@@ -320,7 +323,7 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
                     for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
                         if (p.dbg & 8) break;
                         const uint64_t koff = (uint64_t)((k * TC_UMMA_K * 2) >> 4);   // +32 B per K step
-                        if (pair) {           // 256 x 256 x 16 over the pair: A rows and B (weight) rows are split between the CTAs
+                        if constexpr (pair) { // 256 x 256 x 16 over the pair: A rows and B (weight) rows are split between the CTAs
                             tc_mma2_f16(tmem_d, d_ah + koff, d_wh + koff, idesc, (kb | k) ? 1u : 0u);
                             tc_mma2_f16(tmem_d, d_al + koff, d_wh + koff, idesc, 1u);
                             tc_mma2_f16(tmem_d, d_ah + koff, d_wl + koff, idesc, 1u);
@@ -330,12 +333,12 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
                             tc_mma_f16(tmem_d, d_ah + koff, d_wl + koff, idesc, 1u);
                         }
                     }
-                    if (pair) tc_commit2_mc(&empty_bar[stage], 3);          // both CTAs' stage is free when the pair's MMAs retire
+                    if constexpr (pair) tc_commit2_mc(&empty_bar[stage], 3);     // both CTAs' stage is free when the pair's MMAs retire
                     else if (cs > 1) tc_commit_mc(&empty_bar[stage], mc_mask);   // ... on every CTA of the cluster (their boxes land here too)
                     else tc_commit(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
                     if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
-                if (pair) tc_commit2_mc(&tfull_bar[acc], 3);      // accumulators (one half in each CTA's TMEM) complete -> both epilogues
+                if constexpr (pair) tc_commit2_mc(&tfull_bar[acc], 3);   // accumulators (one half in each CTA's TMEM) complete -> both epilogues
                 else tc_commit(&tfull_bar[acc]);                  // accumulator complete -> epilogue
                 if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
             }
@@ -441,7 +444,7 @@ mapping_layer_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
     if (cs > 1) cluster_sync_all();                    // no CTA leaves while a peer can still signal its barriers
     if (warp == 2) {
         tc_fence_after();
-        if (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if constexpr (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
@@ -611,7 +614,9 @@ int mapping_tc_pack(const float *pw, int n_layers, int dim, void *tc_base, cudaS
 static int tc_ensure_attr() {
     static bool attr_set = false;
     if (!attr_set) {
-        GSB_CHECK_CUDA(cudaFuncSetAttribute(mapping_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(mapping_layer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)TC_SMEM_BYTES));
+        GSB_CHECK_CUDA(cudaFuncSetAttribute(mapping_layer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)TC_SMEM_BYTES));
         attr_set = true;
     }
@@ -644,7 +649,7 @@ static int tc_max_clusters(int cs) {
             at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             int q = 0;
-            if (cudaOccupancyMaxActiveClusters(&q, mapping_layer_tc_kernel, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
+            if (cudaOccupancyMaxActiveClusters(&q, mapping_layer_tc_kernel<false>, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
         }
         cache[cs] = n;
     }
@@ -685,7 +690,8 @@ static int tc_launch_layer(const CUtensorMap &tm_ah, const CUtensorMap &tm_al, c
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    GSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mapping_layer_tc_kernel, tm_ah, tm_al, tm_wh, tm_wl, tm_o0, tm_o1, p));
+    if (pair) GSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mapping_layer_tc_kernel<true>, tm_ah, tm_al, tm_wh, tm_wl, tm_o0, tm_o1, p));
+    else GSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mapping_layer_tc_kernel<false>, tm_ah, tm_al, tm_wh, tm_wl, tm_o0, tm_o1, p));
     return GSB_OK;
 }
 
@@ -765,7 +771,9 @@ int mapping_forward_tc(const float *pb, void *tc_base, int n_layers, int dim,
     // stream (the IPCA chain's 16-CTA cluster kernels), which otherwise wait for a whole layer launch to drain
     const int m_tiles = (int)((n + TC_BLOCK_M - 1) / TC_BLOCK_M);
     // GANSPACE_B200_MAPPING_PAIR=1: CTA pairs issuing tcgen05.mma.cta_group::2 (256 x 256 tiles, each CTA stages half of the
-    // weight tile: 64 B/clk of MMA operand reads and 42 B/clk of TMA fills per SM instead of 96 + 62)
+    // weight tile: 64 B/clk of MMA operand reads and 42 B/clk of TMA fills per SM instead of 96 + 62).  Measured round 2: correct
+    // (1.4e-5 vs fp64, as the 1-CTA form) but SLOWER, 15.9 ms against 11.5 ms for 1.01M rows x 8 layers -- the peer's "my half
+    // has landed" relay through a remote mbarrier arrive sits on the critical path of every stage.  Kept opt-in.
     static int pair_mode = -1;
     if (pair_mode < 0) { const char *e = getenv("GANSPACE_B200_MAPPING_PAIR"); pair_mode = (e && atoi(e) == 1) ? 1 : 0; }
     const int pair = (pair_mode && m_tiles >= 64) ? 1 : 0;
