@@ -252,9 +252,23 @@ __device__ __forceinline__ void sy_epilogue(const EpiParams &e, float4 acc, int6
 #pragma unroll
             for (int o = 0; o < 3; ++o) r[o] += __shfl_xor_sync(0xffffffffu, r[o], off);
         }
-        if ((q & (span - 1)) == 0) {
-            float *dst = e.rgb_out + (b * hw + pix) * 3;
-            atomicAdd(dst, r[0]); atomicAdd(dst + 1, r[1]); atomicAdd(dst + 2, r[2]);
+        float *dst = e.rgb_out + (b * hw + pix) * 3;
+        if (cq <= 32) {
+            // one lane per pixel holds the sum: a plain read-modify-write, deterministic
+            if ((q & (span - 1)) == 0) { dst[0] += r[0]; dst[1] += r[1]; dst[2] += r[2]; }
+        } else {
+            // 256 / 512 channels: the pixel's quads span 2 / 4 warps of this block (blocks hold whole pixels: 256 % cq == 0 and
+            // the launch has no partial blocks); combine them through shared memory in a fixed order
+            __shared__ float rgb_red[8][3];
+            const int wib = threadIdx.x >> 5, wpp = cq >> 5;                    // warp in block, warps per pixel
+            if ((threadIdx.x & 31) == 0) { rgb_red[wib][0] = r[0]; rgb_red[wib][1] = r[1]; rgb_red[wib][2] = r[2]; }
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0 && (wib % wpp) == 0) {
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+                for (int k = 0; k < wpp; ++k) { t0 += rgb_red[wib + k][0]; t1 += rgb_red[wib + k][1]; t2 += rgb_red[wib + k][2]; }
+                dst[0] += t0; dst[1] += t1; dst[2] += t2;
+            }
+            __syncthreads();
         }
     }
     if (e.s_next) {
