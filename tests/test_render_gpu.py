@@ -1,7 +1,9 @@
 """Full synthesis to RGB: every StyledConv of the 1024^2 generator (512 ... 32 channels), the
 ToRGB / skip chain, StyleGAN2.forward with one latent, per-layer latents and style mixing -- against known answers written by
 the unmodified reference (oracle/gen_golden_r2.py G11), plus the reference's own test invariants (tests/partial_forward_test.py:
-partial == full at the hooked layer; tests/layerwise_z_test.py: forward(z) == forward(n_latents * [z]))."""
+partial == full at the hooked layer; tests/layerwise_z_test.py: forward(z) == forward(n_latents * [z])).
+convs.10 .. convs.15 are checked against the reference's full forward: its partial_forward never reaches them (substring match on
+the layer name, wrappers.py:241-246 -- INTEGRATION.md section 3)."""
 import numpy as np
 import pytest
 import torch
