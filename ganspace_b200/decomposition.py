@@ -456,6 +456,12 @@ def compute_arrays(config, instrumented_model, state=None):
         if hasattr(tr, "end_run"):
             tr.end_run()                                # a resident chain kernel never waits for groups that will not come
     tick("sampling + activations + IPCA chain")
+    # host work that does not depend on the chain's result, done while the device still runs the last merge steps (the
+    # export below is the first call that waits for them): get_random_dirs' host stream + upload, the lat_stdev latents
+    device_dirs = layout is not None and config.components * sample_dims >= (1 << 22)
+    pre_dirs = None if device_dirs else \
+        torch.from_numpy(to_native(get_random_dirs(config.components, int(np.prod(sample_shape))))).to(device, non_blocking=True)
+    pre_lat = model.z_to_latent(lat_stdev_z()).reshape(5000, input_dims) if (config.use_w and lat_stdev_z is not None) else None
     X_comp, X_stdev, X_var_ratio = transformer.get_components()
     X_comp = np.array(X_comp, copy=True)
     mean_dev = tr.device_attributes()["mean"]
@@ -487,21 +493,20 @@ def compute_arrays(config, instrumented_model, state=None):
 
     # random projections of the last group's buffer, centred on the global mean (:289-291,312-316)
     n_rand_samples = min(5000, NB if large_d else X.shape[0])
-    if layout is not None and config.components * sample_dims >= (1 << 22):
+    if device_dirs:
         # get_random_dirs' stream (RandomState(2).normal) drawn by the device generator: 42M normals at convs.4
         g = _native.legacy_normal([SEED_RANDOM_DIRS], config.components * sample_dims, device).view(config.components, -1)
         g = g / torch.linalg.vector_norm(g.double(), dim=1, keepdim=True).float()
         dirs_dev = g.view(config.components, lc, lh, lw).permute(0, 2, 3, 1).reshape(config.components, -1).contiguous()
     else:
-        random_dirs = get_random_dirs(config.components, int(np.prod(sample_shape)))
-        dirs_dev = torch.from_numpy(to_native(random_dirs)).to(device)
+        dirs_dev = pre_dirs
     if affine is not None:                                  # dirs . (x - mean) == (dirs Q) . (y - ybar)
         dirs_dev = _native.linear(dirs_dev, affine.Q.T.float().contiguous())
     sub = mean_dev
     if large_d:                                             # the engine centred the last group in place by its batch mean
         sub = mean_dev - tr.last_batch_mean()
         X = tr.last_batch_rows(n_rand_samples)              # (feature shards gathered when distributed)
-    X_stdev_random = _native.project_std(X[:n_rand_samples], dirs_dev, sub=sub).cpu().numpy()
+    rand_std_dev = _native.project_std(X[:n_rand_samples], dirs_dev, sub=sub)       # read back below, with lat_stdev
 
     X_comp = to_nchw(X_comp).reshape(-1, *sample_shape)
     X_global_mean = to_nchw(X_global_mean).reshape(sample_shape)
@@ -510,12 +515,15 @@ def compute_arrays(config, instrumented_model, state=None):
 
     lat_stdev = np.ones_like(X_stdev)
     if config.use_w:
-        if lat_stdev_z is not None:
-            samples = model.z_to_latent(lat_stdev_z()).reshape(5000, input_dims)
+        if pre_lat is not None:
+            samples = pre_lat
         else:
             samples = model.sample_latent(5000).reshape(5000, input_dims)
         zc = torch.from_numpy(Z_comp.reshape(-1, input_dims).astype(np.float32))
-        lat_stdev = _native.project_std(samples.contiguous(), zc).cpu().numpy()
+        both = torch.cat([rand_std_dev.reshape(-1), _native.project_std(samples.contiguous(), zc).reshape(-1)]).cpu().numpy()
+        X_stdev_random, lat_stdev = both[:rand_std_dev.numel()], both[rand_std_dev.numel():]
+    else:
+        X_stdev_random = rand_std_dev.cpu().numpy()
 
     if hasattr(model, "check_numerics"):
         model.check_numerics()

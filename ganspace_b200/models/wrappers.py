@@ -209,13 +209,19 @@ class StyleGAN2(BaseModel):
                                              for _ in range(max(1, int(os.environ.get("GANSPACE_B200_RNG_STREAMS", "1"))))]
         events = []
         seeds_dev = _native.seeds_tensor(list(seeds), self.device)       # ONE host->device copy, before any long kernel is queued
+        # the first group decides when the first partial_fit statistics exist (the merge chain, the critical path of a small-d
+        # run, waits for them): its streams are split over twice as many CTAs (GANSPACE_B200_RNG_FIRST_PARTS)
+        parts0 = parts
         if parts > 1:
+            parts0 = max(parts, min(16, int(os.environ.get("GANSPACE_B200_RNG_FIRST_PARTS", 2 * parts))))
             _native.jump_polys(512 * n_samples, parts, self.device)     # (first use: host computation + upload)
+            _native.jump_polys(512 * n_samples, parts0, self.device)
             # one scratch buffer for the largest group, so that no launch re-allocates it while an earlier one is running
             gmax = max(b - a for a, b in bounds)
+            wsb = _native.load().gsb_legacy_normal_split_workspace_bytes
+            need = max(wsb(gmax, 512 * n_samples, parts), wsb(bounds[0][1] - bounds[0][0], 512 * n_samples, parts0))
             for i, side in enumerate(sides):
-                _native.scratch.get(f"rng_split{i}", _native.load().gsb_legacy_normal_split_workspace_bytes(gmax, 512 * n_samples, parts),
-                                    _native.require_cuda(self.device)).record_stream(side)
+                _native.scratch.get(f"rng_split{i}", need, _native.require_cuda(self.device)).record_stream(side)
         with torch.cuda.device(self.device):
             for side in sides:
                 side.wait_stream(torch.cuda.current_stream())
@@ -223,8 +229,8 @@ class StyleGAN2(BaseModel):
                 side = sides[gi % len(sides)]
                 with torch.cuda.stream(side):
                     _native.legacy_normal(seeds_dev[a:b], 512 * n_samples, self.device,
-                                          out=z[a * n_samples:b * n_samples].view(b - a, 512 * n_samples), parts=parts,
-                                          scratch_key=f"rng_split{gi % len(sides)}")
+                                          out=z[a * n_samples:b * n_samples].view(b - a, 512 * n_samples),
+                                          parts=parts0 if gi == 0 else parts, scratch_key=f"rng_split{gi % len(sides)}")
                     ev = torch.cuda.Event()
                     ev.record(side)
                     events.append(ev)

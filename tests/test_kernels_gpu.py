@@ -130,7 +130,7 @@ def test_batch_stats_vs_oracle(nat, oracle, n, d):
     assert np.max(np.abs(g - g_ref)) < 3e-6 * np.max(np.abs(g_ref))
 
 
-@pytest.mark.parametrize("n,parts", [(20_000, 4), (512 * 1000, 2), (512 * 4000, 3), (512 * 10_000, 8)])
+@pytest.mark.parametrize("n,parts", [(20_000, 4), (512 * 1000, 2), (512 * 4000, 3), (512 * 10_000, 8), (512 * 10_000, 16)])
 def test_legacy_normal_split_streams_bit_exact(nat, oracle, n, parts):
     """A stream generated by several CTAs (MT19937 jump-ahead + order-preserving compaction across sub-streams) is
     bit-identical to the one-CTA stream, which is bit-identical to NumPy's RandomState.standard_normal."""
