@@ -737,28 +737,43 @@ __global__ void embed_h_kernel(const double *__restrict__ hdr, const double *__r
     }
 }
 
-// V[t][i] = sum_s Z[t][s] Q[i][s]  (Z rows = eigenvectors of H), S[t] = sqrt(lam_t)
-__global__ void __launch_bounds__(256)
+// V[t][i] = sum_s Z[t][s] Q[i][s]  (Z rows = eigenvectors of H), S[t] = sqrt(lam_t).  Grid (d / 128, c / 8): a thread owns one
+// feature i and eight components t (this kernel sits on the tail of every run: two 256-thread blocks took 0.93 ms)
+constexpr int ROT_T = 8;
+__global__ void __launch_bounds__(128)
 rotate_kernel(const double *__restrict__ hdr, const double *__restrict__ Z, int n, const double *__restrict__ lam,
               const double *__restrict__ Qbuf, int d, int c, double *__restrict__ V, double *__restrict__ S) {
     if (hdr[2] == 0.0) return;
-    extern __shared__ double zs[];                           // [c][c]
-    const int cp = c + 4;
+    __shared__ double zs[ROT_T][132];                        // this block's ROT_T rows of Z (c <= 128)
+    const int cp = c + 4, t0 = blockIdx.y * ROT_T;
     const double *Q = Qbuf + (size_t)((int)hdr[3]) * d * cp;
-    for (int i = threadIdx.x; i < c * c; i += blockDim.x) zs[i] = Z[(size_t)(i / c) * n + i % c];
+    for (int k = threadIdx.x; k < ROT_T * c; k += blockDim.x) {
+        const int t = k / c, sidx = k % c;
+        zs[t][sidx] = (t0 + t < c) ? Z[(size_t)(t0 + t) * n + sidx] : 0.0;
+    }
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < ROT_T && t0 + threadIdx.x < c) S[t0 + threadIdx.x] = sqrt(fmax(lam[t0 + threadIdx.x], 0.0));
     const int i = blockIdx.x * blockDim.x + threadIdx.x;     // feature index
-    if (blockIdx.x == 0 && threadIdx.x < c) S[threadIdx.x] = sqrt(fmax(lam[threadIdx.x], 0.0));
     if (i >= d) return;
     const double *qrow = Q + (size_t)i * cp;
-    for (int t = 0; t < c; ++t) {
-        double a0 = 0.0, a1 = 0.0;
-        const double *z = zs + (size_t)t * c;
-        int s = 0;
-        for (; s + 1 < c; s += 2) { a0 = fma(z[s], qrow[s], a0); a1 = fma(z[s + 1], qrow[s + 1], a1); }
-        if (s < c) a0 = fma(z[s], qrow[s], a0);
-        V[(size_t)t * d + i] = a0 + a1;
+    double acc0[ROT_T], acc1[ROT_T];
+#pragma unroll
+    for (int t = 0; t < ROT_T; ++t) acc0[t] = acc1[t] = 0.0;
+    // same summation order per output as before: even / odd partial sums, then their sum
+    int sidx = 0;
+    for (; sidx + 1 < c; sidx += 2) {
+        const double q0 = qrow[sidx], q1 = qrow[sidx + 1];
+#pragma unroll
+        for (int t = 0; t < ROT_T; ++t) { acc0[t] = fma(zs[t][sidx], q0, acc0[t]); acc1[t] = fma(zs[t][sidx + 1], q1, acc1[t]); }
     }
+    if (sidx < c) {
+        const double q0 = qrow[sidx];
+#pragma unroll
+        for (int t = 0; t < ROT_T; ++t) acc0[t] = fma(zs[t][sidx], q0, acc0[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < ROT_T; ++t)
+        if (t0 + t < c) V[(size_t)(t0 + t) * d + i] = acc0[t] + acc1[t];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -937,13 +952,9 @@ int materialise_components(double *hdr, double *S, double *V, const double *H, c
     embed_h_kernel<<<1, 256, 0, st>>>(hdr, H, c, n, w.A);
     GSB_CHECK_LAUNCH();
     if (int r = eig_top(w, n, c, w.lam, w.evecs, st)) return r;
-    const size_t smem = (size_t)c * c * sizeof(double);
-    static size_t smem_set = 48 * 1024;
-    if (smem > smem_set) {
-        GSB_CHECK_CUDA(cudaFuncSetAttribute(rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
-    rotate_kernel<<<(d + 255) / 256, 256, smem, st>>>(hdr, w.evecs, n, w.lam, Qbuf, d, c, V, S);
+    GSB_CHECK_ARG(c <= 128, "materialise_components: c <= 128");
+    rotate_kernel<<<dim3((unsigned)((d + 127) / 128), (unsigned)((c + ROT_T - 1) / ROT_T)), 128, 0, st>>>(hdr, w.evecs, n, w.lam, Qbuf, d,
+                                                                                                    c, V, S);
     GSB_CHECK_LAUNCH();
     return sign_rows(V, c, d, st);
 }

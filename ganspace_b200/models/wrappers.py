@@ -143,6 +143,12 @@ class StyleGAN2(BaseModel):
                 f"StyleGAN2 checkpoint {checkpoint} not found and no network access to download it; pass "
                 "random_init=<seed> (or set GANSPACE_B200_RANDOM_INIT) for random-init weights")
 
+    def get_latent_shape(self):
+        """The reference samples one latent for its shape (wrappers.py:60-61).  The draw from the global NumPy stream that this
+        sample_latent(1) consumes is kept (later seeds depend on it); the two kernels behind it are not launched."""
+        _global_seed()
+        return (1, 512)
+
     def sample_latent(self, n_samples=1, seed=None, truncation=None):
         if seed is None:
             seed = _global_seed()
