@@ -168,3 +168,15 @@ def test_style_layer_driver_w_and_z_space(oracle, monkeypatch, tmp_path):
     with np.load(out_path) as data:
         out = {k: data[k] for k in data.files}
     _check_style(out, _expected_style(oracle, fakes.FakeStyleModel(), True), oracle, True)
+
+
+def test_style_layer_driver_four_ranks_gloo(oracle, tmp_path):
+    """W space on four ranks: one ragged round (16 owned slots for the plan's 10 groups), owners with fewer groups than others,
+    the final group's buffer on a rank that does not own it -- the N > 2 control flow of bench.py's scaling run."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import fakes
+    out_path = str(tmp_path / "style4.npz")
+    mp.spawn(_style_worker, args=(4, _free_port(), out_path, True), nprocs=4, join=True)
+    with np.load(out_path) as data:
+        out = {k: data[k] for k in data.files}
+    _check_style(out, _expected_style(oracle, fakes.FakeStyleModel(), True), oracle, True)
