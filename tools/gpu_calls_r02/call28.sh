@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-L="tools/_ab/lib_4e907c2.so tools/_ab/lib_candA.so ganspace_b200/libganspace_b200.so"
+L="tools/gpu_calls_r02/lib_4e907c2.so tools/gpu_calls_r02/lib_candA.so ganspace_b200/libganspace_b200.so"
 echo "== default env" > gpurun_out/ab28.log
 python tools/ab_mapping.py $L >> gpurun_out/ab28.log 2>&1
 echo "== CLUSTER=1" >> gpurun_out/ab28.log

@@ -8,4 +8,4 @@ run GANSPACE_B200_RNG_GROUPS=2,7 GANSPACE_B200_STATS_FIRST=2
 run A=2
 python -m pytest tests/test_e2e_gpu.py -q -m gpu -x --tb=short 2>&1 | tail -3
 GANSPACE_B200_TIMELINE=1 python tools/phase_probe.py 2>&1 | grep -v "chain done" | grep "ms  \|== rep" | head -30
-bash tools/_ab/call33.sh
+bash tools/gpu_calls_r02/call33.sh
