@@ -158,10 +158,31 @@ def _ref_step(w, n_sample, threads):
     return dt, "port"
 
 
+class _StdoutToStderr:
+    """fd-level: whatever the wrapped code (or a library under it) prints to stdout goes to stderr, so that stdout carries
+    the one JSON line only (the reference's model.py prints at import)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    with _StdoutToStderr():
+        line = _reference_line(args)
+    print(line)
+
+
+def _reference_line(args):
     w = _workload(args)
     n_sample = min(args.ref_sample or {1: 10_000, 2: 100_000, 3: 50_000, 4: 4_000, 5: 4_000}[args.config], w["n"])
     n_sample = max(n_sample // w["batch_size"], 1) * w["batch_size"]
@@ -197,7 +218,7 @@ def run_reference(args):
               + ("the unmodified reference (baseline/_ref) through its own decomposition.get_or_compute on the CPU"
                  if kind == "reference" else "oracle port (no reference tree on this box)")
               + f"; {used} threads (fastest of the warm-up sweep {{threads: s}} = { {k: round(v, 2) for k, v in sweep.items()} })")
-    print(json.dumps({
+    return json.dumps({
         "impl": "reference", "metric": METRICS[args.config], "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -205,7 +226,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": used, "host_cores": cores, "kind": kind, "sample": sample,
                          "thread_sweep_s": sweep, "full_n": full},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def _cpu_baseline_subprocess(args):

@@ -372,7 +372,10 @@ class StyleGAN2(BaseModel):
                 syn = self._synthesis(target + 1)
                 res, co = syn.shapes[i]
                 act = syn.forward(w, i + 1).view(-1, res, res, co).permute(0, 3, 1, 2)    # NCHW view of NHWC storage
-                mods[i](_result=act)
+                if mods[i](_result=act) is not act and i < target:
+                    # (an edit on the target layer itself has nothing downstream inside partial_forward)
+                    raise NotImplementedError(f"an edit on layer '{names[i]}' cannot be propagated through the fused synthesis "
+                                              f"chain to '{layer_name}'")
         elif layer_name in names:
             target = names.index(layer_name)
             # the reference computes every to_rgb that precedes the target as well (wrappers.py:232-255)
