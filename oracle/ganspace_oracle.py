@@ -546,8 +546,12 @@ def synthesis_random_init(seed: int = 1234, size: int = 1024, upto: str = "convs
                     act_bias=np.zeros(co, np.float32), upsample=upsample, res_out=res_out)
 
     def to_rgb(ci):
-        rn(1, 3, ci, 1, 1); rn(ci, 512)
+        # ToRGB (:344-363): ModulatedConv2d(ci, 3, 1, demodulate=False) weight randn(1,3,ci,1,1), modulation randn(ci,512) bias 1, bias 0
+        w = rn(1, 3, ci, 1, 1).numpy()[0, :, :, 0, 0]
+        mw = rn(ci, 512).numpy()
+        rgbs.append(dict(weight=w, mod_weight=mw, mod_bias=np.ones(ci, np.float32), bias=np.zeros(3, np.float32)))
 
+    rgbs = []
     layers = {"conv1": styled(ch[4], ch[4], False, 4)}
     to_rgb(ch[4])
     for layer_idx in range((log_size - 2) * 2 + 1):
@@ -563,7 +567,7 @@ def synthesis_random_init(seed: int = 1234, size: int = 1024, upto: str = "convs
         in_ch = out_ch
         if wanted[-1] in layers:
             break
-    return dict(const=const, layers={k: layers[k] for k in wanted})
+    return dict(const=const, layers={k: layers[k] for k in wanted}, to_rgbs=rgbs)     # to_rgbs[0] = to_rgb1, [j + 1] = to_rgbs.j
 
 
 def fixed_noise(seed: int = 0, size: int = 1024):
@@ -681,6 +685,61 @@ def styled_conv_taps(x_nhwc, w, L, noise):
     out = out + float(L["noise_weight"]) * np.asarray(noise, np.float64)[None, :, :, None] + L["act_bias"].astype(np.float64)
     out = np.sqrt(2.0) * np.where(out >= 0, out, 0.2 * out)
     return out
+
+
+def to_rgb_forward(x, w, R, skip=None):
+    """ToRGB (model.py:344-363): 1x1 modulated conv WITHOUT demodulation (ModulatedConv2d(ci, 3, 1, demodulate=False), scale
+    1/sqrt(ci), :219-220,236), + bias, + Upsample(skip) (:33-51: upfirdn2d(skip, [1,3,3,1] outer / 16, up=2, pad=(2,1)),
+    native form op/upfirdn2d.py:157-198: zero insertion, pad, true convolution).  x [B,ci,H,W], w [B,512] -> [B,3,H,W]."""
+    import math
+    import torch
+    import torch.nn.functional as F
+    x = torch.from_numpy(np.ascontiguousarray(x, np.float32))
+    w = torch.from_numpy(np.ascontiguousarray(w, np.float32))
+    B, ci, H, W = x.shape
+    style = F.linear(w, torch.from_numpy(R["mod_weight"]) * (1 / math.sqrt(512)), bias=torch.from_numpy(R["mod_bias"]))
+    weight = (1 / math.sqrt(ci)) * torch.from_numpy(R["weight"]).view(1, 3, ci, 1, 1) * style.view(B, 1, ci, 1, 1)
+    out = F.conv2d(x.reshape(1, B * ci, H, W), weight.view(B * 3, ci, 1, 1), padding=0, groups=B).view(B, 3, H, W)
+    out = out + torch.from_numpy(R["bias"]).view(1, 3, 1, 1)
+    if skip is not None:
+        sk = torch.from_numpy(np.ascontiguousarray(skip, np.float32))
+        h = sk.shape[2]
+        up = torch.zeros(B, 3, 2 * h, 2 * h)
+        up[:, :, ::2, ::2] = sk
+        up = F.pad(up, [2, 1, 2, 1]).reshape(B * 3, 1, 2 * h + 3, 2 * h + 3)
+        kflip = torch.flip(torch.from_numpy(BLUR_K2D), [0, 1]).view(1, 1, 4, 4)
+        out = out + F.conv2d(up, kflip).view(B, 3, 2 * h, 2 * h)
+    return out.numpy()
+
+
+def render_forward(w_layers, params, noises, form: str = "shared", keep=()):
+    """Generator.forward (model.py:493-571) from per-layer W latents ``w_layers`` [B, n_latent, 512] (one global latent: the same
+    row repeated, wrappers.py:202-205): conv1(latent 0) -> to_rgb1(latent 1); per resolution convs[2j](latent 2j+1),
+    convs[2j+1](latent 2j+2), to_rgbs[j](latent 2j+3, skip).  ``params`` = synthesis_random_init(upto = the last StyledConv);
+    returns (image = the last skip, before the wrapper's 0.5 (x + 1), and {name: activation} for the names in ``keep``)."""
+    fn = {"reference": styled_conv_forward, "shared": styled_conv_shared}[form]
+    names = list(params["layers"].keys())
+    B = w_layers.shape[0]
+    kept = {}
+    x = np.repeat(params["const"][None], B, axis=0)
+    x = fn(x, w_layers[:, 0], params["layers"]["conv1"], noises[0])
+    if "conv1" in keep:
+        kept["conv1"] = x
+    skip = to_rgb_forward(x, w_layers[:, 1], params["to_rgbs"][0])
+    if "to_rgb1" in keep:
+        kept["to_rgb1"] = skip
+    i = 1
+    for j in range((len(names) - 1) // 2):
+        for q in range(2):
+            name = f"convs.{2 * j + q}"
+            x = fn(x, w_layers[:, i + q], params["layers"][name], noises[i + q])
+            if name in keep:
+                kept[name] = x
+        skip = to_rgb_forward(x, w_layers[:, i + 2], params["to_rgbs"][j + 1], skip)
+        if f"to_rgbs.{j}" in keep:
+            kept[f"to_rgbs.{j}"] = skip
+        i += 2
+    return skip, kept
 
 
 def synthesis_forward(w, params, noises, upto: str, form: str = "reference"):

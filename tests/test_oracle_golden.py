@@ -151,3 +151,41 @@ def test_small_side_restatement_equals_svd_form(oracle):
     assert np.sum(a.components * b.components, axis=1).min() > 1 - 1e-6
     assert np.allclose(a.singular_values, b.singular_values, rtol=1e-5)
     assert np.allclose(a.explained_variance_ratio, b.explained_variance_ratio, rtol=1e-5) and np.allclose(a.mean, b.mean)
+
+
+def test_render_restatement_vs_reference(oracle, golden, mapping_weights):
+    """Row f2: the oracle's Generator.forward (all 17 StyledConv layers, ToRGB / skip up-sampling, per-layer latents) against
+    the unmodified reference's known answers (oracle/gen_golden_r2.py G11 / G11b): activations of convs.5 .. convs.15, the
+    running skip image after every ToRGB, the final image and a style-mixed image."""
+    from conftest import GOLDEN
+    if not (GOLDEN / "synthesis_deep_known_answers.npz").exists():
+        pytest.skip("fixture synthesis_deep_known_answers.npz not generated")
+    g = golden("synthesis_deep_known_answers.npz")
+    p = oracle.synthesis_random_init(1234, 1024, "convs.15")
+    for i, name in enumerate(str(x) for x in g["conv_names"]):
+        co = p["layers"][name]["weight"].shape[0]
+        p["layers"][name]["noise_weight"] = np.float32(0.1 * (i + 1))
+        p["layers"][name]["act_bias"] = (0.1 * np.sin(np.arange(co, dtype=np.float32) + i)).astype(np.float32)
+    assert len(p["to_rgbs"]) == len(g["rgb_names"]) == 9
+    for i, R in enumerate(p["to_rgbs"]):
+        R["bias"] = (0.05 * np.array([1.0, -2.0, 3.0], np.float32) * (i + 1)).astype(np.float32)
+    noises = oracle.fixed_noise(0, 1024)
+    w = oracle.mapping_forward(g["z"], *mapping_weights)                     # [2, 512]
+    n_lat = 18
+    layers = [f"convs.{i}" for i in range(5, 16)] + [str(x) for x in g["rgb_names"]]
+    img, kept = oracle.render_forward(np.repeat(w[:1, None, :], n_lat, axis=1), p, noises, keep=layers)
+    for layer in layers:
+        act, key = kept[layer], layer.replace(".", "_")
+        assert tuple(act.shape) == tuple(g[f"shape_{key}"]), layer
+        step = max(1, act.shape[-1] // 32)
+        sub = act[:, ::max(1, act.shape[1] // 16), ::step, ::step]
+        ref = g[f"act_{key}_sub"]
+        assert np.abs(sub - ref).max() <= 5e-5 * np.abs(ref).max(), (layer, np.abs(sub - ref).max() / np.abs(ref).max())
+        s2 = (act.astype(np.float64) ** 2).sum()
+        assert abs(s2 - g[f"sum_{key}"][1]) < 1e-4 * g[f"sum_{key}"][1], layer
+    ref_img = g["img_sub"][:1]
+    assert np.abs(0.5 * (img + 1)[:, :, ::4, ::4] - ref_img).max() <= 5e-5 * np.abs(ref_img - 0.5).max()
+    # style mixing: latents 0..7 from z0, 8..17 from z1 (the fixture's forward([z0] * 8 + [z1] * 10))
+    wl = np.concatenate([np.repeat(w[:1, None, :], 8, axis=1), np.repeat(w[1:2, None, :], n_lat - 8, axis=1)], axis=1)
+    mixed, _ = oracle.render_forward(wl, p, noises)
+    assert np.abs(0.5 * (mixed + 1)[:, :, ::4, ::4] - g["mixed_sub"]).max() <= 5e-5 * np.abs(g["mixed_sub"] - 0.5).max()
