@@ -142,6 +142,9 @@ class ClockSampler:
 def _ref_step(w, n_sample, threads):
     """One bounded-sample step of the reference arm -> (seconds, kind)."""
     from oracle import ref_harness as rh
+    # always an explicit thread count: torchrun exports OMP_NUM_THREADS=1 to its workers, which would leave the "all cores"
+    # setting of the sweep single-threaded
+    threads = threads or (os.cpu_count() or 1)
     if rh.ref_dir() is not None:
         with rh.limit_threads(threads):
             dt = rh.run_reference_config(w, n_sample)
