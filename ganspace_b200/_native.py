@@ -62,6 +62,7 @@ SIGNATURES = {
     "gsb_linreg_solve_status": (_I, [_P, _I, _I, _P, _P]),
     "gsb_linreg_normal_matrix": (_P, [_P, _I, _I]),
     "gsb_linreg_solve_pinv": (_I, [_P, _I, _I, _P, _P, _D, _P, _P]),
+    "gsb_ipca_set_chain_mode": (_I, [_I]),
     "gsb_synthesis_packed_bytes": (_Z, [_P, _I, _I]),
     "gsb_synthesis_pack": (_I, [_P, _I, _I, _P, _P, _Z, _P]),
     "gsb_synthesis_workspace_bytes": (_Z, [_P, _I, _L]),
@@ -517,7 +518,7 @@ class IPCAChain:
         # kernels per step: first step = direct solve (8) + seeding of the subspace form (1); later steps = one cluster
         # launch (orthogonal iteration, csrc/subspace.cu).  Shapes outside the subspace kernel's range: direct solve (8).
         subspace = (self.d % 128 == 0 and 128 <= self.d <= 512 and self.c % 8 == 0 and 8 <= self.c <= 128
-                    and os.environ.get("GANSPACE_B200_CHAIN", "") not in ("direct", "lanczos"))
+                    and os.environ.get("GANSPACE_B200_CHAIN", "") not in ("direct", "lanczos") and not _chain_forced_direct)
         instrument.count((1 if self.n_seen > 0 else 9) if subspace else 8)
         self.n_seen += int(n_batch)
 
@@ -605,6 +606,20 @@ class IPCAChain:
         return out
 
 
+class ChainNotConverged(NativeError):
+    """A chain step reached its iteration cap before its residual tolerance (no spectral gap after component c)."""
+
+
+_chain_forced_direct = False
+
+
+def set_chain_mode(direct: bool):
+    """Every chain step enqueued from now on is the exact direct eigen-solve (True) / the default solver (False)."""
+    global _chain_forced_direct
+    _check(load().gsb_ipca_set_chain_mode(1 if direct else 0), "gsb_ipca_set_chain_mode")
+    _chain_forced_direct = bool(direct)
+
+
 def check_eig_status(what: str):
     """Raise if a chain kernel reported a failure since the last check (synchronises the current stream)."""
     flags = C.c_uint(0)
@@ -613,9 +628,10 @@ def check_eig_status(what: str):
         if flags.value & 8:
             raise NativeError(f"{what}: the resident chain kernel waited longer than GANSPACE_B200_CHAIN_TIMEOUT_S for a group's "
                               f"statistics and gave up (status {flags.value})")
-        raise NativeError(f"{what}: a chain step hit its iteration cap without reaching the residual tolerance "
-                          f"(status {flags.value}): the spectrum has no gap after component c; re-run with "
-                          "GANSPACE_B200_CHAIN=direct")
+        raise ChainNotConverged(f"{what}: a chain step hit its iteration cap without reaching the residual tolerance "
+                                f"(status {flags.value}): the spectrum has no gap after component c (numerical rank below "
+                                "n_components?); the exact route is GANSPACE_B200_CHAIN=direct (decomposition.compute re-runs "
+                                "through it by itself)")
 
 
 def sym_eig_top(a: torch.Tensor, c: int):

@@ -1311,7 +1311,11 @@ LanczosWs carve_lanczos(void *base, int d, int c) {
     w.bytes = off;
     return w;
 }
+static int g_chain_force_direct = 0;     // host-side switch, read when a step is enqueued (not thread-safe across handles, as the ABI states)
+bool chain_forced_direct() { return g_chain_force_direct != 0; }
+
 bool lanczos_applicable(int d, int c) {
+    if (chain_forced_direct()) return false;
     // Round 2: the default chain step is the residual-checked orthogonal iteration of subspace.cu; where it does not apply
     // the step is the direct solve of the full d x d problem.  The warm-started block-Lanczos step of round 1 (no
     // convergence check) is an explicit opt-in: GANSPACE_B200_CHAIN=lanczos.
@@ -1463,6 +1467,15 @@ extern "C" int gsb_ipca_chain_step(void *d_state, int d, int c, int64_t n_seen, 
     GSB_CHECK_LAUNCH();
     // the first step seeds the subspace form: Q = V^T, H = diag(S^2)
     if (subspace) return gsb::to_subspace_form(s.hdr, s.S, s.V, s.H, s.Qbuf, d, c, st);
+    return GSB_OK;
+}
+
+// 0 = the environment's choice (default: orthogonal iteration where it applies), 1 = direct solve for every step.
+//   replaces: nothing in the reference (sklearn always solves exactly, _incremental_pca.py:352-368); this is the exact route the
+//   host falls back to when gsb_eig_status reports an iteration cap.
+extern "C" int gsb_ipca_set_chain_mode(int mode) {
+    GSB_CHECK_ARG(mode == 0 || mode == 1, "ipca_set_chain_mode: mode must be 0 or 1");
+    gsb::g_chain_force_direct = mode;
     return GSB_OK;
 }
 

@@ -26,6 +26,9 @@ struct SubspaceWs {
     size_t bytes;
 };
 bool subspace_applicable(int d, int c);
+// gsb_ipca_set_chain_mode(1): every chain step is the direct solve until it is set back to 0 (the host's fallback after a run
+// whose iteration hit its cap, i.e. data without a spectral gap after component c)
+bool chain_forced_direct();
 size_t subspace_smem_bytes(int d, int c);
 SubspaceWs carve_subspace(void *base, int d, int c);
 int subspace_step(double *hdr, double *mean, double *unnorm, double *H, double *Qbuf, const double *mean_b, const double *gram_b,

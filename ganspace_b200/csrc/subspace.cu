@@ -778,6 +778,7 @@ rotate_kernel(const double *__restrict__ hdr, const double *__restrict__ Z, int 
 
 // ------------------------------------------------------------------------------------------------------------------
 bool subspace_applicable(int d, int c) {
+    if (chain_forced_direct()) return false;
     static int mode = -1;
     if (mode == -1) {
         const char *env = getenv("GANSPACE_B200_CHAIN");

@@ -204,7 +204,18 @@ def compute(config, dump_name, instrumented_model):
     timestamp = lambda: datetime.datetime.now().strftime("%d.%m %H:%M")
     print(f"[{timestamp()}] Computing", dump_name.name)
     state = {}
-    arrays = compute_arrays(config, instrumented_model, state)
+    try:
+        arrays = compute_arrays(config, instrumented_model, state)
+    except _native.ChainNotConverged as err:
+        # the iterated chain step found no spectral gap after component c (e.g. activations of numerical rank < n_components):
+        # run again with sklearn's own exact per-step eigen-solve (every rank of a distributed run sees the same status)
+        print(f"{err}\nRe-running with the direct chain step", flush=True)
+        _native.set_chain_mode(True)
+        try:
+            state = {}
+            arrays = compute_arrays(config, instrumented_model, state)
+        finally:
+            _native.set_chain_mode(False)
     if state.get("canceled_at") is not None:
         # Ctrl-C during the fitting loop: the reference saves what was fitted so far under n{gi} and exits 1 (:268-274,342-343)
         dump_name = dump_name.parent / dump_name.name.replace(f"n{state['N']}", f"n{state['canceled_at']}")

@@ -275,3 +275,26 @@ def test_named_direction_pkl_round_trip_and_reference_file(tmp_path):
     assert set(mine["decomposition"]) == set(ref["decomposition"])
     comp2 = directions.load_named_components(str(d), "StyleGAN2", "ffhq", "W")
     assert len(comp2.names) == 2 and np.array_equal(comp2.Z_comp[1], arrays["lat_comp"][2])       # sorted: comp15 < comp2
+
+
+def test_compute_reruns_with_direct_chain_when_the_iteration_reports_no_gap(tmp_path, monkeypatch):
+    """decomposition.compute: a ChainNotConverged from the first pass (gsb_eig_status bit 1) switches the library to the exact
+    direct step for ONE re-run and back (gsb_ipca_set_chain_mode is host-only state: callable without a GPU)."""
+    from types import SimpleNamespace
+    from ganspace_b200 import _native, decomposition
+    seen = []
+
+    def fake_compute_arrays(config, inst, state=None):
+        seen.append(_native._chain_forced_direct)
+        if len(seen) == 1:
+            raise _native.ChainNotConverged("a chain step hit its iteration cap")
+        state["N"] = 10
+        return {"act_comp": np.zeros((1, 1, 2), np.float32)}
+
+    monkeypatch.setattr(decomposition, "compute_arrays", fake_compute_arrays)
+    out = tmp_path / "cache" / "x_n10.npz"
+    decomposition.compute(SimpleNamespace(), out, None)
+    assert seen == [False, True] and _native._chain_forced_direct is False
+    assert out.is_file() and np.load(out)["act_comp"].shape == (1, 1, 2)
+    with pytest.raises(_native.NativeError):
+        _native._check(_native.load().gsb_ipca_set_chain_mode(7), "gsb_ipca_set_chain_mode")
