@@ -447,6 +447,12 @@ def run_ours(args):
                                            note="the same kernel on the same number of rows with nothing else running, measured "
                                                 "after the timed region (median of 3)") if isolated else None)},
             "sections_ms_per_step": {k: v[0] / args.steps for k, v in sections.items()},
+            # strong scaling of ONE job: the sequential merge chain (small-d: replicated on every rank; feature maps: its
+            # small-side eigen-solve) does not shrink with the GPU count -- the residual Amdahl term of the scaling run
+            "amdahl": {"term": "merge chain (sequential rank-c merges; replicated on every rank for d <= 1024, small-side "
+                               "eigen-solve replicated for feature maps)",
+                       "ms_per_step": (sections["chain"][0] / args.steps) if "chain" in sections else None,
+                       "of_ms_per_step": dev_ms},
             "parity": parity,
             "clocks": clocks,
         }
