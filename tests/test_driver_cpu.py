@@ -175,8 +175,9 @@ def test_style_layer_driver_four_ranks_gloo(oracle, tmp_path):
     the final group's buffer on a rank that does not own it -- the N > 2 control flow of bench.py's scaling run."""
     sys.path.insert(0, str(ROOT / "tests"))
     import fakes
-    out_path = str(tmp_path / "style4.npz")
-    mp.spawn(_style_worker, args=(4, _free_port(), out_path, True), nprocs=4, join=True)
-    with np.load(out_path) as data:
-        out = {k: data[k] for k in data.files}
-    _check_style(out, _expected_style(oracle, fakes.FakeStyleModel(), True), oracle, True)
+    for use_w in (True, False):            # False: Z space, the regression pass sharded over the ranks as well
+        out_path = str(tmp_path / f"style4_{int(use_w)}.npz")
+        mp.spawn(_style_worker, args=(4, _free_port(), out_path, use_w), nprocs=4, join=True)
+        with np.load(out_path) as data:
+            out = {k: data[k] for k in data.files}
+        _check_style(out, _expected_style(oracle, fakes.FakeStyleModel(), use_w), oracle, use_w)
