@@ -298,3 +298,42 @@ def test_compute_reruns_with_direct_chain_when_the_iteration_reports_no_gap(tmp_
     assert out.is_file() and np.load(out)["act_comp"].shape == (1, 1, 2)
     with pytest.raises(_native.NativeError):
         _native._check(_native.load().gsb_ipca_set_chain_mode(7), "gsb_ipca_set_chain_mode")
+
+
+def test_plan_and_rounds_properties_hypothesis():
+    """Property test of the host plan: the reference's sizing rules (decomposition.py:198-232,245) for arbitrary (n, B, c), and the
+    sharding invariants the drivers rely on for any world size -- rounds cover every group exactly once and in order, ownership
+    partitions a round with at most ceil(len / world) groups per rank, batch_slots addresses exactly the rows of each owned run."""
+    from hypothesis import given, settings, strategies as st
+    from ganspace_b200 import plan
+
+    @settings(max_examples=300, deadline=None)
+    @given(n=st.integers(1, 3_000_000), B=st.integers(1, 20_000), c=st.integers(1, 1024), world=st.integers(1, 16),
+           g1=st.integers(1, 6), g2=st.integers(1, 12))
+    def check(n, B, c, world, g1, g2):
+        p = plan.make_plan(n, B, c)
+        N = n // B * B
+        NB = max(B, max(2_000, 3 * c))
+        assert (p.N, p.NB, p.n_lat, p.K) == (N, NB, ((N + NB - 1) // B + 1) * B, len(range(0, N, NB)))
+        assert p.n_calls * B == p.n_lat and p.n_lat >= p.K * NB           # the drawn latents cover every (full) group
+        rs = plan.rounds(0, p.K, world, g1, g2)
+        assert [k for r in rs for k in r] == list(range(p.K))
+        for i, rnd in enumerate(rs):
+            assert len(rnd) <= world * (g1 if i == 0 else g2)
+            per = [sum(1 for k in rnd if plan.owner(k, world) == r) for r in range(world)]
+            assert sum(per) == len(rnd) and max(per) <= -(-len(rnd) // world)
+        if p.K and p.K <= 400:
+            for r in range(min(world, 3)):
+                ks = plan.groups_to_process(p, r, world)
+                assert (p.K - 1) in ks and all(plan.owner(k, world) == r or k == p.K - 1 for k in ks)
+                runs = plan.contiguous_runs(ks)
+                needed, offs = plan.batch_slots(p, runs)
+                assert needed == sorted(set(needed)) and all(0 <= b < p.n_calls for b in needed)
+                for run, off in zip(runs, offs):
+                    r0, r1 = p.group_rows(run[0])[0], p.group_rows(run[-1])[1]
+                    # the run's rows are contiguous inside the concatenation of the needed calls, starting at `off`
+                    first_call = r0 // B
+                    assert off == needed.index(first_call) * B + (r0 - first_call * B)
+                    assert needed.index((r1 - 1) // B) - needed.index(first_call) == (r1 - 1) // B - first_call
+
+    check()
